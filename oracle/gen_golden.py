@@ -1,0 +1,186 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz|json by running the UNMODIFIED reference on committed inputs.
+
+Run in the build container (needs /root/reference):   python oracle/gen_golden.py
+
+Inputs come from `delora_b200/synthetic.py` (seeded, deterministic); outputs are what the
+reference's own classes return:
+  utility.projection.ImageProjectionLayer.forward          (src/utility/projection.py:108)
+  preprocessing.normal_computation.NormalsComputer.compute_normal_vectors   (:89)
+  deploy.deployer.Deployer.{transform,rotate}_point_cloud_transformation_matrix  (:181-189)
+  losses.icp_losses.ICPLosses.forward                      (src/losses/icp_losses.py:28)
+  models.model_parts.GeometryHandler.get_transformation_matrix_quaternion (kornia stub, see ref_harness)
+Small cases store full tensors; KITTI-sized cases store SHA-256 digests + scalars so the
+fixtures stay small.  The script also checks the oracle against what it just generated and
+prints the verdict.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from delora_b200 import synthetic  # noqa: E402
+from oracle import ref_harness  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (pair index, w_raw, rings, vfov_deg, H, W)
+    "small_16x180": (0, 192, 16, (-15.0, 15.0), 16, 180),
+    "kitti_64x720": (1, 1875, 64, synthetic.KITTI_VFOV_DEG, 64, 720),
+    "kitti_64x2048": (2, 2048, 64, synthetic.KITTI_VFOV_DEG, 64, 2048),
+}
+
+
+def canonical_projection_outputs(cloud, u, v, idx, stable=False):
+    """The reference sorts by range with an UNSTABLE argsort (src/utility/projection.py:63), so
+    the order among equal-range points is arbitrary.  Canonical forms used for pinning:
+    u, v scattered back to the original point order; idx ordered by (range, index).
+    `torch.argsort` is deterministic for a given input and build, so re-running it here
+    recovers the permutation the reference used."""
+    rng = torch.norm(cloud[None][:, :3, :], dim=1)
+    sort_ref = torch.argsort(rng, dim=1, stable=stable)[0]   # stable=True only for the oracle's outputs
+    u_orig = torch.empty_like(u)
+    v_orig = torch.empty_like(v)
+    u_orig[sort_ref] = u
+    v_orig[sort_ref] = v
+    order = np.lexsort((idx.numpy(), rng[0][idx].numpy()))
+    return u_orig, v_orig, idx[torch.from_numpy(order)]
+
+
+def digest(t):
+    a = t.detach().cpu().contiguous().numpy() if isinstance(t, torch.Tensor) else np.ascontiguousarray(t)
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def ref_pair(ref, cfg, scan_1, scan_2, t_pred, dataset="kitti"):
+    """The reference's own path for one pair: 2x projection, 2x normals, transform, ICP losses,
+    backward to the 4x4 transform."""
+    import deploy.deployer
+    proj = ref.projection.ImageProjectionLayer(config=cfg)
+    nc = ref.normal_computation.NormalsComputer(config=cfg, dataset_name=dataset)
+    out = {}
+    imgs, lists = [], []
+    for k, scan in ((1, scan_1), (2, scan_2)):
+        image, u, v, idx, i2p = proj(input=scan[None].clone(), dataset=dataset)
+        normals, has_n, points = nc.compute_normal_vectors(image=image.clone())
+        uc, vc, idxc = canonical_projection_outputs(scan, u[0], v[0], idx)
+        out[f"image_{k}"], out[f"u_{k}"], out[f"v_{k}"] = image[0], uc, vc
+        out[f"idx_{k}"], out[f"i2p_{k}"] = idxc, i2p[0]
+        out[f"normals_{k}"], out[f"has_normal_{k}"], out[f"points_{k}"] = normals, has_n, points
+        imgs.append(image)
+        lists.append((points, normals))
+    dep = object.__new__(deploy.deployer.Deployer)
+    tm = t_pred.clone().view(1, 4, 4).requires_grad_(True)
+    (p1, n1), (p2, n2) = lists
+    src = dep.transform_point_cloud_transformation_matrix(transformation_matrix=tm,
+                                                          point_cloud=p2.t()[None].contiguous())
+    src_n = dep.rotate_point_cloud_transformation_matrix(transformation_matrix=tm,
+                                                         point_cloud=n2.t()[None].contiguous())
+    icp = ref.icp_losses.ICPLosses(config=cfg)
+    losses, plotting = icp(source_point_cloud_transformed=src, source_normal_list_transformed=src_n,
+                           target_point_cloud=p1.t()[None].contiguous(),
+                           target_normal_list=n1.t()[None].contiguous(),
+                           compute_pointwise_loss_bool=False)
+    loss = cfg["lambda_po2pl"] * losses["loss_po2pl"] + losses["loss_pl2pl"]
+    loss.sum().backward()
+    out["loss_po2pl"] = losses["loss_po2pl"].detach().reshape(1)
+    out["loss_pl2pl"] = losses["loss_pl2pl"].detach().reshape(1)
+    out["grad_T"] = tm.grad[0, :3, :].clone()
+    out["num_pairs"] = torch.tensor([plotting["scan_2_transformed"].shape[2]])
+    out["kept_source_points"] = plotting["scan_2_transformed"][0].detach()
+    return out
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref = ref_harness.reference_modules()
+    from oracle import delora_oracle as orc
+    summary = {}
+    for name, (index, w_raw, rings, vfov, h, w) in CASES.items():
+        cfg = synthetic.fov_config(h=h, w=w, vfov_deg=vfov)
+        scan_1, scan_2, t_gt, t_pred = synthetic.make_pair(index, w_raw=w_raw, rings=rings, vfov_deg=vfov)
+        out = ref_pair(ref, cfg, scan_1, scan_2, t_pred)
+        meta = {"pair_index": index, "w_raw": w_raw, "rings": rings, "vfov_deg": list(vfov), "H": h, "W": w,
+                "n_points": [scan_1.shape[1], scan_2.shape[1]],
+                "K": [int(out["idx_1"].shape[0]), int(out["idx_2"].shape[0])],
+                "P": [int(out["points_1"].shape[0]), int(out["points_2"].shape[0])],
+                "num_pairs": int(out["num_pairs"][0]),
+                "loss_po2pl": float(out["loss_po2pl"][0]), "loss_pl2pl": float(out["loss_pl2pl"][0]),
+                "grad_T": out["grad_T"].numpy().astype(np.float64).tolist(),
+                "inputs_sha256": [digest(scan_1), digest(scan_2)],
+                "sha256": {k: digest(out[k]) for k in
+                           ("image_1", "image_2", "u_1", "v_1", "idx_1", "idx_2",
+                            "normals_1", "normals_2", "has_normal_1", "has_normal_2", "points_1", "points_2")}}
+        if name.startswith("small"):
+            np.savez_compressed(os.path.join(GOLDEN, name + ".npz"),
+                                **{k: v.detach().cpu().numpy() for k, v in out.items()})
+        else:
+            # keep a strided sample of the normals so the GPU parity test has float goldens at size
+            stride = 97
+            np.savez_compressed(os.path.join(GOLDEN, name + "_sample.npz"),
+                                normals_1=out["normals_1"][::stride].numpy(),
+                                points_1=out["points_1"][::stride].numpy(),
+                                has_normal_1=out["has_normal_1"][::stride].numpy(), stride=np.array([stride]))
+        summary[name] = meta
+        # ---- pin the oracle against what the reference just produced
+        o = orc.pair_forward_backward(scan_1, scan_2, t_pred, cfg)
+        img_o = orc.project_to_img(scan_1[None], h, w, cfg["horizontal_field_of_view"],
+                                   cfg["kitti"]["vertical_field_of_view"])
+        checks = {
+            "image_1": torch.equal(o["image_1"][0], out["image_1"]),
+            "image_2": torch.equal(o["image_2"][0], out["image_2"]),
+            "u_1": torch.equal(canonical_projection_outputs(scan_1, img_o[1][0], img_o[2][0], img_o[3], stable=True)[0], out["u_1"]),
+            "v_1": torch.equal(canonical_projection_outputs(scan_1, img_o[1][0], img_o[2][0], img_o[3], stable=True)[1], out["v_1"]),
+            "idx_1": torch.equal(img_o[3], out["idx_1"]),
+            "points_1": torch.equal(o["points_1"], out["points_1"]),
+            "normals_1": torch.equal(o["normals_1"], out["normals_1"]),
+            "normals_2": torch.equal(o["normals_2"], out["normals_2"]),
+            "num_pairs": o["num_pairs"] == meta["num_pairs"],
+            "loss_po2pl_rel": abs(o["loss_po2pl"] - meta["loss_po2pl"]) / meta["loss_po2pl"],
+            "loss_pl2pl_rel": abs(o["loss_pl2pl"] - meta["loss_pl2pl"]) / meta["loss_pl2pl"],
+            "grad_T_rel": float((o["grad_T"] - out["grad_T"]).abs().max() / out["grad_T"].abs().max()),
+        }
+        print(name, json.dumps(checks))
+    # ---- projection-only stress clouds (full tensors, tiny)
+    for name, cloud, (h, w, vfov) in (
+            ("edge_16x180", synthetic.edge_stress_cloud(), (16, 180, (-15.0, 15.0))),
+            ("tie_16x512", synthetic.tie_stress_cloud(), (16, 512, (-15.0, 15.0)))):
+        cfg = synthetic.fov_config(h=h, w=w, vfov_deg=vfov)
+        proj = ref.projection.ImageProjectionLayer(config=cfg)
+        image, u, v, idx, i2p = proj(input=cloud[None].clone(), dataset="kitti")
+        uc, vc, idxc = canonical_projection_outputs(cloud, u[0], v[0], idx)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), cloud=cloud.numpy(), image=image[0].numpy(),
+                            u=uc.numpy(), v=vc.numpy(), idx=idxc.numpy())
+        io = orc.project_to_img(cloud[None], h, w, cfg["horizontal_field_of_view"],
+                                cfg["kitti"]["vertical_field_of_view"])
+        print(name, "image", torch.equal(io[0], image), "idx", torch.equal(io[3], idxc),
+              "idx_mismatch", int((io[3] != idxc).sum()) if io[3].shape == idxc.shape else "shape")
+        summary[name] = {"H": h, "W": w, "vfov_deg": list(vfov), "K": int(idx.shape[0])}
+    # ---- quaternion -> T (kornia 0.3.0 restatement) vs the in-repo quat2mat and scipy
+    g = torch.Generator().manual_seed(7)
+    quat = torch.randn(16, 4, generator=g)
+    trans = torch.randn(16, 3, generator=g)
+    t_ref = ref.model_parts.GeometryHandler.get_transformation_matrix_quaternion(
+        translation=trans, quaternion=quat, device="cpu")
+    from scipy.spatial.transform import Rotation
+    r_scipy = torch.from_numpy(Rotation.from_quat(quat.numpy().astype(np.float64)).as_matrix()).float()
+    print("quat: kornia-stub vs scipy max abs", float((t_ref[:, :3, :3] - r_scipy).abs().max()))
+    np.savez_compressed(os.path.join(GOLDEN, "quaternion.npz"), quaternion=quat.numpy(), translation=trans.numpy(),
+                        T=t_ref.numpy())
+    summary["_versions"] = {"torch": torch.__version__, "numpy": np.__version__,
+                            "scipy": __import__("scipy").__version__, "numba": __import__("numba").__version__,
+                            "reference": "leggedrobotics/delora @ 15a25ee (SURVEY.md header)"}
+    with open(os.path.join(GOLDEN, "golden.json"), "w") as f:
+        json.dump(summary, f, indent=1)
+    print("written to", GOLDEN)
+
+
+if __name__ == "__main__":
+    main()
