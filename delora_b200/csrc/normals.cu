@@ -1,0 +1,182 @@
+// Per-pixel surface normals of a range image (sm_100a).
+//
+// Replaces preprocessing.normal_computation.NormalsComputer.compute_normal_vectors
+// (reference: src/preprocessing/normal_computation.py:89-122 gather of the (2a+1)x(2b+1)
+// edge-clamped patch; :53-87 range gate, >= min neighbours, eigen-decomposition, orientation)
+// and utility.linalg.cov (src/utility/linalg.py:33-56 zero-aware mean / covariance).
+//
+// One CTA stages a (TH+2a) x (TW+2b) tile of (x, y, z, |p|) as float4 in shared memory (one
+// LDS.128 per tap), every thread owns one pixel: pass 1 = gated sum and count, pass 2 = centred
+// covariance (same two-pass arithmetic as the reference), then a cyclic Jacobi eigen-solve of the
+// 3x3 covariance in registers, smallest-eigenvalue eigenvector, flipped toward the sensor.
+// The kernel is FP32-issue / shared-memory bound (~2.4 kFLOP per pixel against 28 B of HBM
+// traffic), not HBM bound; see DESIGN.md.
+#include "common.cuh"
+
+namespace delora {
+
+constexpr int kNormTW = 32;
+constexpr int kNormTH = 8;
+
+struct Sym3 { float a00, a01, a02, a11, a12, a22; };
+
+// Cyclic Jacobi for a symmetric 3x3; returns the eigenvector of the smallest eigenvalue.
+__device__ __forceinline__ void smallest_eigenvector(Sym3 m, float& nx, float& ny, float& nz) {
+    float a[3][3] = {{m.a00, m.a01, m.a02}, {m.a01, m.a11, m.a12}, {m.a02, m.a12, m.a22}};
+    float v[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+#pragma unroll 1
+    for (int sweep = 0; sweep < 8; ++sweep) {
+        const float off = fabsf(a[0][1]) + fabsf(a[0][2]) + fabsf(a[1][2]);
+        const float diag = fabsf(a[0][0]) + fabsf(a[1][1]) + fabsf(a[2][2]);
+        if (off <= 1e-12f * diag || off == 0.0f) break;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int p = (k == 2) ? 1 : 0;
+            const int q = (k == 0) ? 1 : 2;
+            const float apq = a[p][q];
+            if (apq == 0.0f) continue;
+            const float theta = (a[q][q] - a[p][p]) / (2.0f * apq);
+            const float t = copysignf(1.0f, theta) / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.0f)));
+            const float c = rsqrtf(fmaf(t, t, 1.0f));
+            const float s = t * c;
+            const float tau = s / (1.0f + c);
+            a[p][p] -= t * apq;
+            a[q][q] += t * apq;
+            a[p][q] = 0.0f; a[q][p] = 0.0f;
+            const int r = 3 - p - q;
+            const float arp = a[r][p], arq = a[r][q];
+            a[r][p] = arp - s * (arq + tau * arp);
+            a[r][q] = arq + s * (arp - tau * arq);
+            a[p][r] = a[r][p]; a[q][r] = a[r][q];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float vip = v[i][p], viq = v[i][q];
+                v[i][p] = vip - s * (viq + tau * vip);
+                v[i][q] = viq + s * (vip - tau * viq);
+            }
+        }
+    }
+    int j = 0;
+    float best = a[0][0];
+    if (a[1][1] < best) { best = a[1][1]; j = 1; }
+    if (a[2][2] < best) { j = 2; }
+    nx = (j == 0) ? v[0][0] : (j == 1 ? v[0][1] : v[0][2]);
+    ny = (j == 0) ? v[1][0] : (j == 1 ? v[1][1] : v[1][2]);
+    nz = (j == 0) ? v[2][0] : (j == 1 ? v[2][1] : v[2][2]);
+    const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
+    nx *= inv; ny *= inv; nz *= inv;
+}
+
+// A, B: half sizes of the patch when known at compile time (loops unroll); -1 = runtime.
+template <int A_, int B_>
+__global__ void __launch_bounds__(kNormTW * kNormTH)
+normals_kernel(const float* __restrict__ image, int C_img, int H, int W, int a_rt, int b_rt,
+               float eps_range, int min_nb, float* __restrict__ normals) {
+    extern __shared__ float4 tile[];
+    const int a = (A_ >= 0) ? A_ : a_rt;
+    const int b = (B_ >= 0) ? B_ : b_rt;
+    const int tw = kNormTW + 2 * b, th = kNormTH + 2 * a;
+    const int bi = blockIdx.z;
+    const int u0 = blockIdx.x * kNormTW, v0 = blockIdx.y * kNormTH;
+    const size_t HW = (size_t)H * W;
+    const float* __restrict__ img = image + (size_t)bi * C_img * HW;
+
+    // stage the halo tile; out-of-image positions are never addressed (neighbour coordinates are
+    // clamped to the image first, normal_computation.py:104-111), so they are left unset.
+    for (int i = threadIdx.x; i < tw * th; i += kNormTW * kNormTH) {
+        const int ly = i / tw, lx = i - ly * tw;
+        const int gv = v0 - a + ly, gu = u0 - b + lx;
+        if (gv >= 0 && gv < H && gu >= 0 && gu < W) {
+            const size_t o = (size_t)gv * W + gu;
+            const float x = __ldg(img + o), y = __ldg(img + HW + o), z = __ldg(img + 2 * HW + o);
+            tile[i] = make_float4(x, y, z, range3(x, y, z));
+        }
+    }
+    __syncthreads();
+
+    const int lu = threadIdx.x % kNormTW, lv = threadIdx.x / kNormTW;
+    const int u = u0 + lu, v = v0 + lv;
+    if (u >= W || v >= H) return;
+    const float4 c = tile[(lv + a) * tw + (lu + b)];
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    if (c.x != 0.0f && c.y != 0.0f && c.z != 0.0f) {                  // normal_computation.py:35
+        const int ntaps = (2 * a + 1) * (2 * b + 1);
+        // clamped window in tile coordinates
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        int n = 0;
+#pragma unroll 1
+        for (int dv = -a; dv <= a; ++dv) {
+            const int vv = min(max(v + dv, 0), H - 1) - (v0 - a);
+            const float4* __restrict__ row = tile + vv * tw;
+#pragma unroll
+            for (int du = -b; du <= b; ++du) {
+                const int uu = min(max(u + du, 0), W - 1) - (u0 - b);
+                const float4 q = row[uu];
+                const bool gated = fabsf(q.w - c.w) > eps_range;          // :56-59
+                const bool present = !gated && ((q.x != 0.0f) | (q.y != 0.0f) | (q.z != 0.0f));   // linalg.py:34-37
+                if (present) { sx += q.x; sy += q.y; sz += q.z; ++n; }
+            }
+        }
+        if (n >= min_nb) {                                            // :67-69
+            const float k = (float)ntaps, fn = (float)n;
+            // torch.mean(dim) * K / n   (linalg.py:41-42)
+            const float mx = __fdiv_rn(__fmul_rn(__fdiv_rn(sx, k), k), fn);
+            const float my = __fdiv_rn(__fmul_rn(__fdiv_rn(sy, k), k), fn);
+            const float mz = __fdiv_rn(__fmul_rn(__fdiv_rn(sz, k), k), fn);
+            Sym3 s = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int dv = -a; dv <= a; ++dv) {
+                const int vv = min(max(v + dv, 0), H - 1) - (v0 - a);
+                const float4* __restrict__ row = tile + vv * tw;
+#pragma unroll
+                for (int du = -b; du <= b; ++du) {
+                    const int uu = min(max(u + du, 0), W - 1) - (u0 - b);
+                    const float4 q = row[uu];
+                    const bool gated = fabsf(q.w - c.w) > eps_range;
+                    const bool present = !gated && ((q.x != 0.0f) | (q.y != 0.0f) | (q.z != 0.0f));
+                    if (present) {
+                        const float dx = q.x - mx, dy = q.y - my, dz = q.z - mz;    // linalg.py:43-46
+                        s.a00 = fmaf(dx, dx, s.a00); s.a01 = fmaf(dx, dy, s.a01); s.a02 = fmaf(dx, dz, s.a02);
+                        s.a11 = fmaf(dy, dy, s.a11); s.a12 = fmaf(dy, dz, s.a12); s.a22 = fmaf(dz, dz, s.a22);
+                    }
+                }
+            }
+            const float f = __fdiv_rn(1.0f, (float)(n - 1));           // linalg.py:39, :56
+            s.a00 *= f; s.a01 *= f; s.a02 *= f; s.a11 *= f; s.a12 *= f; s.a22 *= f;
+            smallest_eigenvector(s, nx, ny, nz);                      // torch.symeig, evec[:, :, 0]  (:70-76)
+            if (nx * c.x + ny * c.y + nz * c.z > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }   // :79-81
+        }
+    }
+    float* __restrict__ out = normals + (size_t)bi * 3 * HW + (size_t)v * W + u;
+    out[0] = nx; out[HW] = ny; out[2 * HW] = nz;
+}
+
+}  // namespace delora
+
+using namespace delora;
+
+extern "C" int delora_normals_fwd(const float* image, int B, int C_img, int H, int W, int nb_h, int nb_w,
+                                  float epsilon_range, int min_neighbors, float* normals, void* stream) {
+    DELORA_CHECK_ARG(image && normals, "delora_normals_fwd: null pointer");
+    DELORA_CHECK_ARG(B > 0 && B <= 65535 && C_img >= 3 && H > 0 && W > 0, "delora_normals_fwd: bad shape");
+    const int a = nb_h / 2, b = nb_w / 2;                              // int(side/2): normal_computation.py:97-98
+    DELORA_CHECK_ARG(a >= 0 && b >= 0 && a <= 16 && b <= 32, "delora_normals_fwd: neighbourhood %dx%d unsupported",
+                     nb_h, nb_w);
+    const size_t smem = (size_t)(kNormTW + 2 * b) * (kNormTH + 2 * a) * sizeof(float4);
+    dim3 grid((W + kNormTW - 1) / kNormTW, (H + kNormTH - 1) / kNormTH, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a == 3 && b == 5) {
+        normals_kernel<3, 5><<<grid, kNormTW * kNormTH, smem, st>>>(image, C_img, H, W, a, b, epsilon_range,
+                                                                    min_neighbors, normals);
+    } else {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(normals_kernel<-1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem);
+            DELORA_CHECK_ARG(e == cudaSuccess, "delora_normals_fwd: smem opt-in failed: %s", cudaGetErrorString(e));
+        }
+        normals_kernel<-1, -1><<<grid, kNormTW * kNormTH, smem, st>>>(image, C_img, H, W, a, b, epsilon_range,
+                                                                      min_neighbors, normals);
+    }
+    DELORA_CHECK_LAUNCH("normals_kernel");
+    return 0;
+}

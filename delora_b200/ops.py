@@ -1,0 +1,203 @@
+"""Tensor-level wrappers over the C ABI: one call = one operator over a whole batch.
+
+Every function takes CUDA tensors, allocates its outputs with torch (device memory is the
+plumbing torch provides), passes raw pointers + the current stream to libdelora_b200.so and
+returns tensors.  Nothing here computes on the host and nothing falls back to torch ops.
+"""
+import torch
+
+from . import _lib
+
+LOSS_PO2PO, LOSS_PO2PL, LOSS_PL2PL, NORMAL_LINEAR = 1, 2, 4, 8
+LOSS_ROW, ICP_PARTIAL = 8, 40
+
+_keys_cache = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError(f"{name}: expected a contiguous CUDA tensor of dtype {dtype}, got "
+                         f"{getattr(t, 'dtype', type(t))} on {getattr(t, 'device', '?')}")
+    return t.data_ptr()
+
+
+def _keys(device, b, hw):
+    """All-ones uint64 key scratch; delora_project_fwd leaves it all-ones again."""
+    k = (device.index, b, hw)
+    buf = _keys_cache.get(k)
+    if buf is None:
+        buf = torch.full((b, hw), -1, dtype=torch.int64, device=device)
+        _keys_cache[k] = buf
+    return buf
+
+
+def project(points, n_points, h, w, hfov, vfov, div_mode=0):
+    """points [B,C,N] fp32, n_points [B] int32 -> image [B,C+1,H,W], index_map [B,H,W] int32.
+    (src/utility/projection.py:48-106)"""
+    b, c, n = points.shape
+    image = torch.empty((b, c + 1, h, w), dtype=torch.float32, device=points.device)
+    index_map = torch.empty((b, h, w), dtype=torch.int32, device=points.device)
+    keys = _keys(points.device, b, h * w)
+    L = _lib.lib()
+    _lib.check(L.delora_project_fwd(_req(points, torch.float32, "points"), _req(n_points, torch.int32, "n_points"),
+                                    b, c, n, h, w, float(hfov[0]), float(hfov[1]), float(vfov[0]), float(vfov[1]),
+                                    int(div_mode), keys.data_ptr(), image.data_ptr(), index_map.data_ptr(),
+                                    _stream()), "delora_project_fwd")
+    return image, index_map
+
+
+def project_uv(points, n_points, h, w, hfov, vfov, div_mode=0):
+    """(u, v, range) of every point in the original order: three [B,N] fp32 tensors."""
+    b, c, n = points.shape
+    u = torch.zeros((b, n), dtype=torch.float32, device=points.device)
+    v = torch.zeros_like(u)
+    r = torch.zeros_like(u)
+    L = _lib.lib()
+    _lib.check(L.delora_project_uv(_req(points, torch.float32, "points"), _req(n_points, torch.int32, "n_points"),
+                                   b, c, n, h, w, float(hfov[0]), float(hfov[1]), float(vfov[0]), float(vfov[1]),
+                                   int(div_mode), u.data_ptr(), v.data_ptr(), r.data_ptr(), _stream()),
+               "delora_project_uv")
+    return u, v, r
+
+
+def sort_by_range(rng, n_points):
+    """rng [B,N] fp32 -> order [B,N] int32: indices in ascending (range, index) order."""
+    b, n = rng.shape
+    L = _lib.lib()
+    order = torch.empty((b, n), dtype=torch.int32, device=rng.device)
+    scratch = torch.empty((int(L.delora_sort_scratch_bytes(b, n)),), dtype=torch.uint8, device=rng.device)
+    _lib.check(L.delora_sort_by_range(_req(rng, torch.float32, "range"), _req(n_points, torch.int32, "n_points"),
+                                      b, n, order.data_ptr(), scratch.data_ptr(), _stream()), "delora_sort_by_range")
+    return order
+
+
+def normals(image, neighborhood=(7, 11), epsilon_range=0.5, min_neighbors=10):
+    """image [B,C,H,W] -> normals [B,3,H,W] (src/preprocessing/normal_computation.py:89-122)."""
+    b, c, h, w = image.shape
+    out = torch.empty((b, 3, h, w), dtype=torch.float32, device=image.device)
+    L = _lib.lib()
+    _lib.check(L.delora_normals_fwd(_req(image, torch.float32, "image"), b, c, h, w, int(neighborhood[0]),
+                                    int(neighborhood[1]), float(epsilon_range), int(min_neighbors),
+                                    out.data_ptr(), _stream()), "delora_normals_fwd")
+    return out
+
+
+def lists_from_images(image, normals_img):
+    """-> pts4 [B,HW,4], nrm4 [B,HW,4], cell_start [B,HW+1] int32, counts [B] int32."""
+    b, c, h, w = image.shape
+    hw = h * w
+    dev = image.device
+    pts4 = torch.empty((b, hw, 4), dtype=torch.float32, device=dev)
+    nrm4 = torch.empty((b, hw, 4), dtype=torch.float32, device=dev)
+    cell_start = torch.empty((b, hw + 1), dtype=torch.int32, device=dev)
+    counts = torch.empty((b,), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    scratch = torch.empty((b * L.delora_scan_blocks(hw),), dtype=torch.int32, device=dev)
+    _lib.check(L.delora_lists_from_images(_req(image, torch.float32, "image"),
+                                          _req(normals_img, torch.float32, "normals"), b, c, h, w,
+                                          pts4.data_ptr(), nrm4.data_ptr(), cell_start.data_ptr(),
+                                          counts.data_ptr(), scratch.data_ptr(), _stream()),
+               "delora_lists_from_images")
+    return pts4, nrm4, cell_start, counts
+
+
+def grid_build(pts, nrm, n, h, w, hfov, vfov):
+    """pts, nrm [B,3,N] channels-first lists, n [B] int32 -> cell-sorted pts4, nrm4 [B,N,4], cell_start."""
+    b, _, ns = pts.shape
+    hw = h * w
+    dev = pts.device
+    pts4 = torch.empty((b, ns, 4), dtype=torch.float32, device=dev)
+    nrm4 = torch.empty((b, ns, 4), dtype=torch.float32, device=dev)
+    cell_start = torch.empty((b, hw + 1), dtype=torch.int32, device=dev)
+    cursor = torch.empty((b, hw), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    scratch = torch.empty((b * L.delora_scan_blocks(hw),), dtype=torch.int32, device=dev)
+    _lib.check(L.delora_grid_build(_req(pts, torch.float32, "pts"),
+                                   _req(nrm, torch.float32, "nrm") if nrm is not None else None,
+                                   _req(n, torch.int32, "n"), b, ns, h, w, float(hfov[0]), float(hfov[1]),
+                                   float(vfov[0]), float(vfov[1]), pts4.data_ptr(), nrm4.data_ptr(),
+                                   cell_start.data_ptr(), cursor.data_ptr(), scratch.data_ptr(), _stream()),
+               "delora_grid_build")
+    return pts4, nrm4, cell_start
+
+
+def pack_lists(pts, nrm, n):
+    b, _, ns = pts.shape
+    pts4 = torch.empty((b, ns, 4), dtype=torch.float32, device=pts.device)
+    nrm4 = torch.empty((b, ns, 4), dtype=torch.float32, device=pts.device)
+    L = _lib.lib()
+    _lib.check(L.delora_pack_lists(_req(pts, torch.float32, "pts"),
+                                   _req(nrm, torch.float32, "nrm") if nrm is not None else None,
+                                   _req(n, torch.int32, "n"), b, ns, pts4.data_ptr(), nrm4.data_ptr(), _stream()),
+               "delora_pack_lists")
+    return pts4, nrm4
+
+
+def icp_fwd_bwd(src_pts4, src_nrm4, n_src, transform, tgt_pts4, tgt_nrm4, cell_start, h, w, hfov, vfov,
+                lambda_po2pl=1.0, flags=LOSS_PO2PL | LOSS_PL2PL, pointwise=False, partials=None):
+    """Fused transform + exact NN + losses + gradient.  transform: [B,12] (3x4 row-major) or None.
+    -> losses [B,8], grad_T [B,12], (nn_index [B,Ns] int32, point_dir, normal_dir [B,Ns,4]) or Nones."""
+    b, ns, _ = src_pts4.shape
+    nt = tgt_pts4.shape[1]
+    dev = src_pts4.device
+    L = _lib.lib()
+    losses = torch.empty((b, LOSS_ROW), dtype=torch.float32, device=dev)
+    grad_t = torch.empty((b, 12), dtype=torch.float32, device=dev)
+    if partials is None:
+        partials = torch.empty((b * L.delora_icp_blocks(ns) * ICP_PARTIAL,), dtype=torch.float32, device=dev)
+    nn_index = point_dir = normal_dir = None
+    if pointwise:
+        nn_index = torch.empty((b, ns), dtype=torch.int32, device=dev)
+        point_dir = torch.empty((b, ns, 4), dtype=torch.float32, device=dev)
+        normal_dir = torch.empty((b, ns, 4), dtype=torch.float32, device=dev)
+    _lib.check(L.delora_icp_fwd_bwd(
+        _req(src_pts4, torch.float32, "src_pts4"), _req(src_nrm4, torch.float32, "src_nrm4"),
+        _req(n_src, torch.int32, "n_src"), ns,
+        _req(transform, torch.float32, "transform") if transform is not None else None,
+        _req(tgt_pts4, torch.float32, "tgt_pts4"), _req(tgt_nrm4, torch.float32, "tgt_nrm4"),
+        _req(cell_start, torch.int32, "cell_start"), nt, b, h, w,
+        float(hfov[0]), float(hfov[1]), float(vfov[0]), float(vfov[1]), float(lambda_po2pl), int(flags),
+        losses.data_ptr(), grad_t.data_ptr(),
+        nn_index.data_ptr() if pointwise else None, point_dir.data_ptr() if pointwise else None,
+        normal_dir.data_ptr() if pointwise else None, partials.data_ptr(), _stream()), "delora_icp_fwd_bwd")
+    return losses, grad_t, nn_index, point_dir, normal_dir
+
+
+def icp_point_grads(point_dir, normal_dir, n_src, losses, upstream):
+    """-> grad_pts, grad_nrm [B,3,Ns] channels-first."""
+    b, ns, _ = point_dir.shape
+    gp = torch.empty((b, 3, ns), dtype=torch.float32, device=point_dir.device)
+    gn = torch.empty((b, 3, ns), dtype=torch.float32, device=point_dir.device)
+    L = _lib.lib()
+    _lib.check(L.delora_icp_point_grads(_req(point_dir, torch.float32, "point_dir"),
+                                        _req(normal_dir, torch.float32, "normal_dir"),
+                                        _req(n_src, torch.int32, "n_src"), ns, b,
+                                        _req(losses, torch.float32, "losses"),
+                                        _req(upstream, torch.float32, "upstream"),
+                                        gp.data_ptr(), gn.data_ptr(), _stream()), "delora_icp_point_grads")
+    return gp, gn
+
+
+def quat_to_T(quaternion, translation):
+    b = quaternion.shape[0]
+    t = torch.empty((b, 4, 4), dtype=torch.float32, device=quaternion.device)
+    L = _lib.lib()
+    _lib.check(L.delora_quat_to_T(_req(quaternion, torch.float32, "quaternion"),
+                                  _req(translation, torch.float32, "translation"), b, t.data_ptr(), _stream()),
+               "delora_quat_to_T")
+    return t
+
+
+def quat_to_T_bwd(quaternion, grad_t):
+    b = quaternion.shape[0]
+    gq = torch.empty((b, 4), dtype=torch.float32, device=quaternion.device)
+    gt = torch.empty((b, 3), dtype=torch.float32, device=quaternion.device)
+    L = _lib.lib()
+    _lib.check(L.delora_quat_to_T_bwd(_req(quaternion, torch.float32, "quaternion"),
+                                      _req(grad_t, torch.float32, "grad_T"), b, gq.data_ptr(), gt.data_ptr(),
+                                      _stream()), "delora_quat_to_T_bwd")
+    return gq, gt

@@ -1,0 +1,105 @@
+"""Batched scan-pair hot path: raw scans -> range images -> normals -> lists -> fused ICP
+losses + gradient w.r.t. the predicted transform.  One launch per operator for the whole batch,
+all buffers preallocated (no allocation, no host sync inside a step; CUDA-graph capturable).
+
+This is what `Deployer.step` does per sample with Python loops and host round trips
+(src/deploy/deployer.py:245-268 projection, :290-312 transform + ICPLosses), with the normals
+computed in-line from the projected image as the reference's preprocessing does
+(src/preprocessing/preprocesser.py:52,60-61).
+"""
+import torch
+
+from . import _lib, ops
+
+
+class ScanPairPipeline:
+    def __init__(self, batch, n_max, h, w, hfov, vfov, device="cuda", channels=3, neighborhood=(7, 11),
+                 epsilon_range=0.5, min_neighbors=10, lambda_po2pl=1.0,
+                 flags=ops.LOSS_PO2PL | ops.LOSS_PL2PL, div_mode=0):
+        self.B, self.N, self.H, self.W, self.C = int(batch), int(n_max), int(h), int(w), int(channels)
+        self.hfov, self.vfov = (float(hfov[0]), float(hfov[1])), (float(vfov[0]), float(vfov[1]))
+        self.nb, self.eps, self.min_nb = tuple(neighborhood), float(epsilon_range), int(min_neighbors)
+        self.lam, self.flags, self.div_mode = float(lambda_po2pl), int(flags), int(div_mode)
+        self.device = torch.device(device)
+        self.L = _lib.lib()
+        if self.device.type != "cuda":
+            raise RuntimeError("delora_b200 runs on CUDA devices only (no CPU fallback)")
+        b2, hw, dev = 2 * self.B, self.H * self.W, self.device
+        f32, i32 = torch.float32, torch.int32
+        self.points = torch.zeros((b2, self.C, self.N), dtype=f32, device=dev)     # [scan_1 x B | scan_2 x B]
+        self.n_points = torch.zeros((b2,), dtype=i32, device=dev)
+        self.keys = torch.full((b2, hw), -1, dtype=torch.int64, device=dev)
+        self.image = torch.empty((b2, self.C + 1, self.H, self.W), dtype=f32, device=dev)
+        self.index_map = torch.empty((b2, self.H, self.W), dtype=i32, device=dev)
+        self.normals = torch.empty((b2, 3, self.H, self.W), dtype=f32, device=dev)
+        self.pts4 = torch.empty((b2, hw, 4), dtype=f32, device=dev)
+        self.nrm4 = torch.empty((b2, hw, 4), dtype=f32, device=dev)
+        self.cell_start = torch.empty((b2, hw + 1), dtype=i32, device=dev)
+        self.counts = torch.empty((b2,), dtype=i32, device=dev)
+        self.scan_scratch = torch.empty((b2 * self.L.delora_scan_blocks(hw),), dtype=i32, device=dev)
+        self.transform = torch.zeros((self.B, 12), dtype=f32, device=dev)
+        self.losses = torch.empty((self.B, ops.LOSS_ROW), dtype=f32, device=dev)
+        self.grad_T = torch.empty((self.B, 12), dtype=f32, device=dev)
+        self.partials = torch.empty((self.B * self.L.delora_icp_blocks(hw) * ops.ICP_PARTIAL,), dtype=f32,
+                                    device=dev)
+        self.launches_per_step = 2 + 1 + 2 + 2   # scatter+resolve, normals, count+emit, icp+finalize
+
+    def load(self, scans_1, scans_2, transforms):
+        """Host-side staging helper for tests: lists of [3,N_i] tensors + [B,4,4] transforms."""
+        for i, (s1, s2) in enumerate(zip(scans_1, scans_2)):
+            self.points[i, :, :s1.shape[1]] = s1.to(self.device)
+            self.points[self.B + i, :, :s2.shape[1]] = s2.to(self.device)
+            self.n_points[i] = s1.shape[1]
+            self.n_points[self.B + i] = s2.shape[1]
+        self.transform.copy_(transforms[:, :3, :].reshape(self.B, 12).to(self.device))
+
+    OPERATORS = ("projection", "normals", "lists", "icp")
+
+    def step(self, events=None):
+        """Enqueue the whole hot path on the current stream; returns (losses [B,8], grad_T [B,12]).
+        `events`: optional list of 5 torch.cuda.Event (timing enabled) recorded before the first and
+        after each of the four operators, for per-kernel timing inside a measured region."""
+        L, st = self.L, torch.cuda.current_stream().cuda_stream
+        if events is not None:
+            events[0].record()
+        b2, B, H, W, hw = 2 * self.B, self.B, self.H, self.W, self.H * self.W
+        hf, vf = self.hfov, self.vfov
+        _lib.check(L.delora_project_fwd(self.points.data_ptr(), self.n_points.data_ptr(), b2, self.C, self.N, H, W,
+                                        hf[0], hf[1], vf[0], vf[1], self.div_mode, self.keys.data_ptr(),
+                                        self.image.data_ptr(), self.index_map.data_ptr(), st), "delora_project_fwd")
+        if events is not None:
+            events[1].record()
+        _lib.check(L.delora_normals_fwd(self.image.data_ptr(), b2, self.C + 1, H, W, self.nb[0], self.nb[1],
+                                        self.eps, self.min_nb, self.normals.data_ptr(), st), "delora_normals_fwd")
+        if events is not None:
+            events[2].record()
+        _lib.check(L.delora_lists_from_images(self.image.data_ptr(), self.normals.data_ptr(), b2, self.C + 1, H, W,
+                                              self.pts4.data_ptr(), self.nrm4.data_ptr(),
+                                              self.cell_start.data_ptr(), self.counts.data_ptr(),
+                                              self.scan_scratch.data_ptr(), st), "delora_lists_from_images")
+        if events is not None:
+            events[3].record()
+        # source = scan_2 (second half), target = scan_1 (first half): deployer.py:294-307
+        f4 = 16
+        _lib.check(L.delora_icp_fwd_bwd(self.pts4.data_ptr() + B * hw * f4, self.nrm4.data_ptr() + B * hw * f4,
+                                        self.counts.data_ptr() + B * 4, hw, self.transform.data_ptr(),
+                                        self.pts4.data_ptr(), self.nrm4.data_ptr(), self.cell_start.data_ptr(), hw,
+                                        B, H, W, hf[0], hf[1], vf[0], vf[1], self.lam, self.flags,
+                                        self.losses.data_ptr(), self.grad_T.data_ptr(), None, None, None,
+                                        self.partials.data_ptr(), st), "delora_icp_fwd_bwd")
+        if events is not None:
+            events[4].record()
+        return self.losses, self.grad_T
+
+    def algorithmic_bytes(self, k_points=None):
+        """Algorithmic bytes per launch of each operator (SURVEY.md §8(d) per-unit figures x the units
+        one launch processes).  k_points: mean valid pixels per scan (K)."""
+        b2, B, hw, c = 2 * self.B, self.B, self.H * self.W, self.C
+        k = float(k_points) if k_points is not None else float(hw)
+        n = float(self.N)
+        return {
+            "projection": b2 * (4 * c * n + 4 * (c + 1) * hw + 4 * hw),          # read xyz, write image + index map
+            "normals": b2 * (12 * hw + 12 * hw),                                   # read xyz image, write normals
+            "lists": b2 * (12 * hw + 12 * hw + 32 * k + 4 * hw),                   # read image+normals, write 2 float4 lists + CSR
+            "icp": B * ((16 * hw + 12 * k + 4 * k) + (12 * k + 12 * k + 4 * k + 24 * k)),   # NN search + fused loss (K=M)
+        }

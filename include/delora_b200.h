@@ -1,0 +1,195 @@
+/*
+ * delora_b200 — C ABI of the B200-native (sm_100a) DeLORA hot path.
+ *
+ * The reference (leggedrobotics/delora) is pure Python with no FFI layer of its own; its
+ * operator surface for this path is the set of Python methods cited on each entry point
+ * below (paths relative to the reference root).  Every function here is what a ctypes
+ * binding of that method calls; `delora_b200/_lib.py` is that binding and INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch allocates), unless the
+ *     parameter name starts with `h_`;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream); all
+ *     work is enqueued on it and nothing synchronises the device;
+ *   - return value: 0 = ok, non-zero = error; `delora_last_error()` returns a thread-local,
+ *     NUL-terminated description of the last failure on the calling thread;
+ *   - no global mutable state: scratch memory is passed in by the caller.  Functions are
+ *     re-entrant per stream.
+ *   - batches: `B` independent scans / scan pairs per call, one launch per operator for the
+ *     whole batch.  Variable-length lists are padded to a stride with a device-side count.
+ */
+#ifndef DELORA_B200_H_
+#define DELORA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DELORA_B200_ABI_VERSION 1
+
+/* float4-packed list element: (x, y, z, tag).  `tag` is an int32 bit pattern or a float flag,
+ * as documented per array. */
+typedef struct { float x, y, z, w; } delora_f4;
+
+/* loss switches (config/hyperparameters.yaml:14-19) */
+#define DELORA_LOSS_PO2PO        1u   /* point_to_point_loss                 */
+#define DELORA_LOSS_PO2PL        2u   /* point_to_plane_loss                 */
+#define DELORA_LOSS_PL2PL        4u   /* plane_to_plane_loss                 */
+#define DELORA_NORMAL_LINEAR     8u   /* normal_loss: "linear" (default "squared") */
+
+/* number of floats in one row of the `losses` output of delora_icp_fwd_bwd */
+#define DELORA_LOSS_ROW 8   /* [po2po, po2pl, pl2pl, M_pairs, M_po2po, 0, 0, 0] */
+/* number of floats per block-partial row in the icp workspace */
+#define DELORA_ICP_PARTIAL 40
+
+int         delora_abi_version(void);
+const char* delora_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Spherical projection.
+ * Replaces utility.projection.ImageProjectionLayer.project_to_img
+ *   (src/utility/projection.py:48-106; (u,v): :21-31; dedupe: :34-43).
+ *
+ * points     [B, C, n_stride] fp32 channels-first (x, y, z, extra channels...)
+ * n_points   [B] int32 (device): valid points of each scan (<= n_stride)
+ * keys       [B, H*W] uint64 scratch.  MUST be all-ones (0xFF bytes) on entry; it is all-ones
+ *            again on exit (the resolve pass resets it), so one memset at allocation suffices.
+ * image      [B, C+1, H, W] fp32 out: channels of the closest point per pixel + its range;
+ *            empty pixels are 0.
+ * index_map  [B, H, W] int32 out: index (into the scan) of the point kept in the pixel, -1 if empty.
+ * hfov/vfov  radians, as the reference's bin scripts hand them over (bin/run_training.py:62-67).
+ * div_mode   0: (a - f0) / span   (torch CPU op sequence, the golden vectors)
+ *            1: (a - f0) * (1/span)  (torch CUDA's scalar-divide kernel) — see DESIGN.md.
+ * Tie rule: equal fp32 range in one pixel -> lowest point index wins.
+ */
+int delora_project_fwd(const float* points, const int32_t* n_points, int B, int C, int n_stride,
+                       int H, int W, double hfov0, double hfov1, double vfov0, double vfov1,
+                       int div_mode, uint64_t* keys, float* image, int32_t* index_map, void* stream);
+
+/* (u, v) of every point, un-rounded, in the ORIGINAL point order (the reference returns them
+ * permuted by its range sort; see delora_sort_by_range).  src/utility/projection.py:21-31.
+ * u, v: [B, n_stride] fp32 out; range: [B, n_stride] fp32 out (may be NULL). */
+int delora_project_uv(const float* points, const int32_t* n_points, int B, int C, int n_stride,
+                      int H, int W, double hfov0, double hfov1, double vfov0, double vfov1,
+                      int div_mode, float* u, float* v, float* range, void* stream);
+
+/* Stable ascending sort of each scan's points by fp32 range (ties: lower index first):
+ * the order `torch.argsort(range)` imposes in src/utility/projection.py:63-67, made
+ * deterministic.  LSD radix sort, 4 passes of 8 bits, one launch set for the batch.
+ * range      [B, n_stride] fp32 (non-negative; NaN sorts last)
+ * order      [B, n_stride] int32 out: point indices in ascending (range, index) order
+ * scratch    bytes >= delora_sort_scratch_bytes(B, n_stride)
+ */
+int64_t delora_sort_scratch_bytes(int B, int n_stride);
+int delora_sort_by_range(const float* range, const int32_t* n_points, int B, int n_stride,
+                         int32_t* order, void* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-pixel normals.
+ * Replaces preprocessing.normal_computation.NormalsComputer.compute_normal_vectors
+ *   (src/preprocessing/normal_computation.py:89-122, :53-87) and utility.linalg.cov
+ *   (src/utility/linalg.py:33-56).
+ *
+ * image      [B, C_img, H, W] fp32 (first three channels are x, y, z)
+ * nb_h, nb_w neighbourhood side lengths (7, 11); patch = (2*(nb_h/2)+1) x (2*(nb_w/2)+1), edge-clamped
+ * normals    [B, 3, H, W] fp32 out; 0 where the pixel is not valid (x!=0 & y!=0 & z!=0) or has
+ *            fewer than `min_neighbors` range-gated neighbours.
+ */
+int delora_normals_fwd(const float* image, int B, int C_img, int H, int W, int nb_h, int nb_w,
+                       float epsilon_range, int min_neighbors, float* normals, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Image -> lists (row-major order of the valid pixels), the layout the reference stores and
+ * trains on (src/preprocessing/normal_computation.py:30-41, :84-87;
+ * src/preprocessing/preprocesser.py:64-68), plus the cell index used by the NN search.
+ *
+ * pts4       [B, H*W] out: (x, y, z, bits(pixel id))    for the P_b valid pixels, in order
+ * nrm4       [B, H*W] out: (nx, ny, nz, has_normal ? 1 : 0)
+ * cell_start [B, H*W + 1] int32 out: exclusive prefix of the valid flags (CSR over pixels)
+ * counts     [B] int32 out: P_b
+ * scratch    int32 [B * delora_scan_blocks(H*W)]
+ */
+int delora_scan_blocks(int n_cells);
+int delora_lists_from_images(const float* image, const float* normals, int B, int C_img, int H, int W,
+                             delora_f4* pts4, delora_f4* nrm4, int32_t* cell_start, int32_t* counts,
+                             int32_t* scratch, void* stream);
+
+/* Bin arbitrary point lists (the reference's [1,3,N] tensors) into the spherical cell grid:
+ * counting sort by cell.  Needed by losses.icp_losses.ICPLosses.forward for lists that did
+ * not come from delora_lists_from_images (src/losses/icp_losses.py:34 builds a cKDTree here).
+ * Points outside the field of view are clamped into the border cells (the search stays exact).
+ *
+ * pts, nrm   [B, 3, n_stride] fp32 channels-first;  n [B] int32
+ * pts4/nrm4  [B, n_stride] out, sorted by cell; pts4.w = bits(original list index)
+ * cell_start [B, H*W+1] int32 out
+ * cursor     [B, H*W] int32 scratch (any contents), scratch int32 [B*delora_scan_blocks(H*W)]
+ */
+int delora_grid_build(const float* pts, const float* nrm, const int32_t* n, int B, int n_stride,
+                      int H, int W, double hfov0, double hfov1, double vfov0, double vfov1,
+                      delora_f4* pts4, delora_f4* nrm4, int32_t* cell_start, int32_t* cursor,
+                      int32_t* scratch, void* stream);
+
+/* Pack channels-first lists to float4 (no sorting): pts4.w = bits(list index), nrm4.w = has_normal. */
+int delora_pack_lists(const float* pts, const float* nrm, const int32_t* n, int B, int n_stride,
+                      delora_f4* pts4, delora_f4* nrm4, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused SE(3) transform + exact nearest neighbour + ICP losses, forward and backward.
+ * Replaces, per scan pair:
+ *   deploy.deployer.Deployer.{transform,rotate}_point_cloud_transformation_matrix  (src/deploy/deployer.py:181-189)
+ *   losses.icp_losses.ICPLosses.forward          (src/losses/icp_losses.py:28-158; cKDTree :34, query :24-26)
+ *   KDPointToPlaneLoss / KDPlaneToPlaneLoss / KDPointToPointLoss   (:196-206, :224-240, :168-179)
+ *   and autograd's backward of those down to the 3x4 transform.
+ *
+ * src_pts4/src_nrm4 [B, src_stride]: source points / normals BEFORE the transform (nrm4.w ignored;
+ *                   has-normal is decided on the rotated normal as the reference does, :48-50)
+ * n_src             [B] int32
+ * T                 [B, 12] fp32 row-major 3x4 (R | t); NULL = identity (inputs already transformed)
+ * tgt_pts4/tgt_nrm4 [B, tgt_stride] sorted by cell (from delora_lists_from_images / delora_grid_build)
+ * cell_start        [B, H*W+1]
+ * lambda_po2pl      weight of the po2pl term in the gradient (deployer.py:310)
+ * flags             DELORA_LOSS_* bits
+ * losses            [B, DELORA_LOSS_ROW] out (unweighted means, as ICPLosses returns them)
+ * grad_T            [B, 12] out: d(po2po + lambda*po2pl + pl2pl)/d(R|t), row-major 3x4
+ * nn_index          [B, src_stride] int32 out or NULL: tag (tgt_pts4.w bits) of the NN of every source point
+ * point_dir         [B, src_stride] float4 out or NULL: unscaled d(loss)/d(source point): r*n_t with w = 1 for a
+ *                   kept (normal, normal) pair; (s - t) with w = 2 for a po2po pair; w = 0 otherwise
+ * normal_dir        [B, src_stride] float4 out or NULL: unscaled d(pl2pl)/d(source normal)
+ *                   (delora_icp_point_grads turns the two into the reference-shaped gradients)
+ * partials          fp32 scratch [B * delora_icp_blocks(src_stride) * DELORA_ICP_PARTIAL]
+ * The NN is the exact float64 Euclidean nearest neighbour (lowest tag on exact ties).
+ */
+int delora_icp_blocks(int src_stride);
+int delora_icp_fwd_bwd(const delora_f4* src_pts4, const delora_f4* src_nrm4, const int32_t* n_src,
+                       int src_stride, const float* T,
+                       const delora_f4* tgt_pts4, const delora_f4* tgt_nrm4, const int32_t* cell_start,
+                       int tgt_stride, int B, int H, int W,
+                       double hfov0, double hfov1, double vfov0, double vfov1,
+                       float lambda_po2pl, uint32_t flags,
+                       float* losses, float* grad_T, int32_t* nn_index,
+                       delora_f4* point_dir, delora_f4* normal_dir,
+                       float* partials, void* stream);
+
+/* Backward of ICPLosses.forward w.r.t. its two differentiable inputs, for callers that hand in
+ * already-transformed clouds and let autograd continue (src/deploy/deployer.py:294-307 -> :341):
+ * upstream [B,3] = d(total)/d(loss_po2po, loss_po2pl, loss_pl2pl);  losses = the row written by
+ * delora_icp_fwd_bwd;  grad_pts, grad_nrm: [B, 3, src_stride] channels-first out. */
+int delora_icp_point_grads(const delora_f4* point_dir, const delora_f4* normal_dir, const int32_t* n_src,
+                           int src_stride, int B, const float* losses, const float* upstream,
+                           float* grad_pts, float* grad_nrm, void* stream);
+
+/* quaternion (x, y, z, w) + translation -> 4x4, and its backward.
+ * Replaces models.model_parts.GeometryHandler.get_transformation_matrix_quaternion
+ *   (src/models/model_parts.py:37-44 -> kornia 0.3.0 quaternion_to_rotation_matrix).
+ * quaternion [B,4], translation [B,3] -> T [B,16].  grad variant: gT [B,16] -> gq [B,4], gt [B,3]. */
+int delora_quat_to_T(const float* quaternion, const float* translation, int B, float* T, void* stream);
+int delora_quat_to_T_bwd(const float* quaternion, const float* grad_T, int B,
+                         float* grad_quaternion, float* grad_translation, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DELORA_B200_H_ */

@@ -44,13 +44,16 @@ def compute_2d_coordinates(point_cloud, width_pixel, height_pixel, hfov, vfov):
     return u, v
 
 
-def project_to_img(point_cloud, height_pixel, width_pixel, hfov, vfov, device="cpu"):
+def project_to_img(point_cloud, height_pixel, width_pixel, hfov, vfov, device="cpu", uv_override=None):
     """src/utility/projection.py:48-106.
 
     point_cloud [1,C,N] -> (image [1,C+1,H,W], u [1,N], v [1,N], point_indices [K] int64
     ascending range, image_to_pointcloud_indices [1,K,2] int64 (v,u)).
     `device` only selects where the torch float ops run (the tests also run this on "cuda" to
     compare against what the reference computes with its default ``device: "cuda"``).
+    `uv_override=(u, v)` ([N] each, ORIGINAL point order) replaces the computed float coordinates;
+    the tests use it to check the integer stage (min-range selection, scatter, indices) of the
+    CUDA kernel bit-exactly on the kernel's own (u, v).
     """
     point_cloud = point_cloud.to(device)
     b, c, n = point_cloud.shape
@@ -60,6 +63,9 @@ def project_to_img(point_cloud, height_pixel, width_pixel, hfov, vfov, device="c
     sort_indices = torch.argsort(pcr[:, c, :], dim=1, stable=True)        # :63 (stable: see header)
     pcr = pcr[:, :, sort_indices[0]]                                      # :67
     u, v = compute_2d_coordinates(pcr, width_pixel, height_pixel, hfov, vfov)   # :69
+    if uv_override is not None:
+        u = uv_override[0].to(device)[sort_indices[0]][None]
+        v = uv_override[1].to(device)[sort_indices[0]][None]
     ru, rv = torch.round(u), torch.round(v)
     inside = (ru <= width_pixel - 1) & (ru >= 0) & (rv <= height_pixel - 1) & (rv >= 0)   # :74-75
     u_f = ru[inside].long().cpu().numpy()                                 # :76-77, :87-88

