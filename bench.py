@@ -56,39 +56,44 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled through NVML every 5 ms while the timed regions run
+    (the B200_PROFILING.md `nvidia-smi --query-gpu=clocks.sm,...` line, without the process spawn)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index):
+    def __init__(self, device_index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.samples, self.reason_bits, self._stop_evt, self.handle, self.max_mhz = [], 0, threading.Event(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                      # clocks are evidence, not a dependency of the run
+            self.error = repr(e)
 
     def run(self):
+        if self.handle is None:
+            return
+        nv = self.nv
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                parts = [x.strip() for x in out.stdout.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.005)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        reasons = set()
-        for s in self.samples:
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": float(self.samples[0][1]) if self.samples else None,
-                "samples": len(self.samples), "reasons": sorted(reasons)}
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                "reasons": sorted(name for bit, name in self.REASONS.items() if self.reason_bits & bit)}
 
 
 def make_inputs(rank, n_sets):
@@ -194,7 +199,7 @@ def run_ours(args):
     for i in range(Wm):
         pipes[i % ROTATE].step()
     torch.cuda.synchronize()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     sampler = ClockSampler(local)
     sampler.start()
     barrier(world)
@@ -205,12 +210,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     barrier(world)
     t_wall = time.perf_counter() - t_wall
-    total_ms = ev[0][0].elapsed_time(ev[K - 1][4])
+    total_ms = ev[0][0].elapsed_time(ev[K - 1][3])
     op_ms = {name: sum(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(K)) / K
              for j, name in enumerate(ScanPairPipeline.OPERATORS)}
     total_ms = max_over_ranks(total_ms, world, device)
     value = world * PAIRS_PER_GPU * K / (total_ms * 1e-3)
-    counts = pipes[0].counts.float().mean().item()
+    counts = (pipes[0].pts_grid[:, :, 3].view(torch.int32) >= 0).sum(dim=1).float().mean().item()
     losses0 = pipes[0].losses[0].tolist()
 
     # ---------------- end to end from pinned host buffers (`e2e`) -----------------------------
@@ -328,7 +333,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-pairs", type=int, default=3, help="pairs timed for the cpu_baseline leg (0 = skip)")

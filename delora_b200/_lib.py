@@ -21,14 +21,18 @@ SIGNATURES = {
     "delora_sort_scratch_bytes": (c_i64, [c_int, c_int]),
     "delora_sort_by_range": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "delora_normals_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
-                                   c_void_p]),
+                                   c_void_p, c_void_p, c_void_p]),
     "delora_scan_blocks": (c_int, [c_int]),
     "delora_lists_from_images": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p]),
     "delora_grid_build": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
                                   c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "delora_pack_lists": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "delora_icp_blocks": (c_int, [c_int]),
+    "delora_icp_partial_rows": (c_int, [c_int]),
+    "delora_icp_scratch_floats": (c_i64, [c_int, c_int]),
+    "delora_icp_dense_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_double, c_double, c_double, c_double, c_float, c_u32, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
     "delora_icp_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_float,
                                    c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

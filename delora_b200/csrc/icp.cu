@@ -12,38 +12,17 @@
 // PROVEN exact by a geometric guard: every unsearched target lies beyond one of the window's
 // four borders (two half-planes of constant azimuth, two cones of constant elevation), so it is
 // at least  min(r_xy*sin(d_az), r*sin(d_el))  away; if the best distance found is below that
-// bound the window result is the global NN, otherwise the window doubles (up to the whole grid).
+// bound the window result is the global NN, otherwise the window grows strip by strip on its weakest side (up to the whole grid).
 // Candidates are pre-filtered in fp32 and ranked in fp64 (ties: lowest tag), like cKDTree.
-#include "common.cuh"
+#include "icp_common.cuh"
 
 namespace delora {
 
 constexpr int kIcpThreads = 256;
-constexpr float kHalfPiF = 1.57079632679489661923f;
-
-struct NNBest {
-    double d2;
-    float d2f;     // fp32 upper bound of d2 used by the prefilter
-    int pos;       // position in the sorted target list
-    int tag;       // tgt_pts4[pos].w bits
-};
 
 __device__ __forceinline__ void nn_scan_range(const float4* __restrict__ tp, int j0, int j1, float sx, float sy,
                                               float sz, NNBest& best) {
-    for (int j = j0; j < j1; ++j) {
-        const float4 t = __ldg(tp + j);
-        const float dx = sx - t.x, dy = sy - t.y, dz = sz - t.z;
-        const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d2f <= best.d2f) {
-            const double ex = (double)sx - (double)t.x, ey = (double)sy - (double)t.y, ez = (double)sz - (double)t.z;
-            const double d2 = ex * ex + ey * ey + ez * ez;
-            const int tag = __float_as_int(t.w);
-            if (d2 < best.d2 || (d2 == best.d2 && tag < best.tag)) {
-                best.d2 = d2; best.pos = j; best.tag = tag;
-                best.d2f = __double2float_ru(d2) * 1.00001f;
-            }
-        }
-    }
+    for (int j = j0; j < j1; ++j) nn_eval(__ldg(tp + j), j, sx, sy, sz, best);
 }
 
 // scan the cells [c0, c1] (unwrapped column indices, c1 - c0 + 1 <= W) of one grid row
@@ -68,7 +47,7 @@ __device__ __forceinline__ void nn_scan_cols(const float4* __restrict__ tp, cons
 __device__ __forceinline__ NNBest nn_search(const GridParams& g, const float4* __restrict__ tp,
                                             const int32_t* __restrict__ cs, float sx, float sy, float sz) {
     NNBest best;
-    best.d2 = 1.0e300; best.d2f = 3.0e38f; best.pos = -1; best.tag = 0x7fffffff;
+    nn_init(best);
     const int H = g.H, W = g.W;
     if (cs[(size_t)H * W] == 0) return best;
     float us, vs;
@@ -105,7 +84,7 @@ __device__ __forceinline__ NNBest nn_search(const GridParams& g, const float4* _
         }
         const float bmin = fminf(fminf(b_dn, b_up), fminf(b_lf, b_rt));
         if (bmin >= kInf) break;                                           // the window is the whole grid
-        if (best.pos >= 0 && __double2float_ru(sqrt(best.d2)) <= bmin * 0.9995f) break;
+        if (best.pos >= 0 && nn_best_dist_ub(best) <= bmin * 0.9995f) break;
         if (bmin == b_dn) {
             --r_lo;
             nn_scan_cols(tp, cs + (size_t)r_lo * W, W, c_lo, c_hi, sx, sy, sz, best);
@@ -127,18 +106,13 @@ __device__ __forceinline__ NNBest nn_search(const GridParams& g, const float4* _
     return best;
 }
 
-// Partial layout (DELORA_ICP_PARTIAL = 40 floats per block):
-//  0 sum r^2            1 sum pl2pl term      2 M
-//  3..5   sum r*n_t                 6..14  sum (r*n_t) p^T
-//  15..23 sum g_n m^T               24 sum |s-t|^2 (po2po)   25 M'
-//  26..28 sum (s-t)                 29..37 sum (s-t) p^T      38,39 pad
 template <bool HAS_T>
 __global__ void __launch_bounds__(kIcpThreads)
 icp_kernel(const float4* __restrict__ src_pts4, const float4* __restrict__ src_nrm4, const int32_t* __restrict__ n_src,
            int src_stride, const float* __restrict__ T, const float4* __restrict__ tgt_pts4,
            const float4* __restrict__ tgt_nrm4, const int32_t* __restrict__ cell_start, int tgt_stride, GridParams g,
            uint32_t flags, int32_t* __restrict__ nn_index, float4* __restrict__ point_dir,
-           float4* __restrict__ normal_dir, float* __restrict__ partials) {
+           float4* __restrict__ normal_dir, float* __restrict__ partial_rows, int rows_per_pair) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * kIcpThreads + threadIdx.x;
     const bool active = i < n_src[b];
@@ -146,117 +120,73 @@ icp_kernel(const float4* __restrict__ src_pts4, const float4* __restrict__ src_n
     const float4* __restrict__ tn = tgt_nrm4 + (size_t)b * tgt_stride;
     const int32_t* __restrict__ cs = cell_start + (size_t)b * ((size_t)g.H * g.W + 1);
 
-    float acc[38];
-#pragma unroll
-    for (int k = 0; k < 38; ++k) acc[k] = 0.0f;
-
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), m = p, tq = p, tnq = p;
+    float sx = 0.f, sy = 0.f, sz = 0.f, nsx = 0.f, nsy = 0.f, nsz = 0.f;
+    bool paired = false;
     if (active) {
-        const float4 p = __ldg(src_pts4 + (size_t)b * src_stride + i);
-        const float4 m = __ldg(src_nrm4 + (size_t)b * src_stride + i);
-        float sx, sy, sz, nsx, nsy, nsz;
+        p = __ldg(src_pts4 + (size_t)b * src_stride + i);
+        m = __ldg(src_nrm4 + (size_t)b * src_stride + i);
         if (HAS_T) {
-            const float* __restrict__ t = T + (size_t)b * 12;
-            const float r00 = __ldg(t + 0), r01 = __ldg(t + 1), r02 = __ldg(t + 2), tx = __ldg(t + 3);
-            const float r10 = __ldg(t + 4), r11 = __ldg(t + 5), r12 = __ldg(t + 6), ty = __ldg(t + 7);
-            const float r20 = __ldg(t + 8), r21 = __ldg(t + 9), r22 = __ldg(t + 10), tz = __ldg(t + 11);
-            // R p (+ t afterwards, as deployer.py:185-188 does it)
-            sx = fmaf(r02, p.z, fmaf(r01, p.y, r00 * p.x)) + tx;
-            sy = fmaf(r12, p.z, fmaf(r11, p.y, r10 * p.x)) + ty;
-            sz = fmaf(r22, p.z, fmaf(r21, p.y, r20 * p.x)) + tz;
-            nsx = fmaf(r02, m.z, fmaf(r01, m.y, r00 * m.x));
-            nsy = fmaf(r12, m.z, fmaf(r11, m.y, r10 * m.x));
-            nsz = fmaf(r22, m.z, fmaf(r21, m.y, r20 * m.x));
+            const Rigid rt = load_rigid(T + (size_t)b * 12);
+            apply_rigid(rt, p, m, sx, sy, sz, nsx, nsy, nsz);
         } else {
             sx = p.x; sy = p.y; sz = p.z; nsx = m.x; nsy = m.y; nsz = m.z;
         }
         const NNBest best = nn_search(g, tp, cs, sx, sy, sz);
         if (nn_index) nn_index[(size_t)b * src_stride + i] = best.pos >= 0 ? best.tag : -1;
-        float4 pd = make_float4(0.f, 0.f, 0.f, 0.f), nd = make_float4(0.f, 0.f, 0.f, 0.f);
         if (best.pos >= 0) {
-            const float4 t = __ldg(tp + best.pos);
-            const float4 q = __ldg(tn + best.pos);
-            const bool src_has = (nsx != 0.0f) | (nsy != 0.0f) | (nsz != 0.0f);         // icp_losses.py:48-50
-            const bool tgt_has = q.w != 0.0f;                                            // :51-52
-            const float dx = sx - t.x, dy = sy - t.y, dz = sz - t.z;
-            if (src_has && tgt_has) {                                                    // :110-121
-                acc[2] = 1.0f;
-                if (flags & DELORA_LOSS_PO2PL) {
-                    const float r = fmaf(dz, q.z, fmaf(dy, q.y, dx * q.x));              // :197-199
-                    acc[0] = r * r;
-                    const float gx = r * q.x, gy = r * q.y, gz = r * q.z;
-                    acc[3] = gx; acc[4] = gy; acc[5] = gz;
-                    acc[6] = gx * p.x; acc[7] = gx * p.y; acc[8] = gx * p.z;
-                    acc[9] = gy * p.x; acc[10] = gy * p.y; acc[11] = gy * p.z;
-                    acc[12] = gz * p.x; acc[13] = gz * p.y; acc[14] = gz * p.z;
-                    pd = make_float4(gx, gy, gz, 1.0f);
-                }
-                if (flags & DELORA_LOSS_PL2PL) {
-                    float hx, hy, hz;
-                    if (flags & DELORA_NORMAL_LINEAR) {                                  // :226-231
-                        const float om = 1.0f - fmaf(nsz, q.z, fmaf(nsy, q.y, nsx * q.x));
-                        acc[1] = om * om;
-                        hx = -om * q.x; hy = -om * q.y; hz = -om * q.z;
-                    } else {                                                             // :232-238
-                        hx = nsx - q.x; hy = nsy - q.y; hz = nsz - q.z;
-                        acc[1] = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
-                    }
-                    acc[15] = hx * m.x; acc[16] = hx * m.y; acc[17] = hx * m.z;
-                    acc[18] = hy * m.x; acc[19] = hy * m.y; acc[20] = hy * m.z;
-                    acc[21] = hz * m.x; acc[22] = hz * m.y; acc[23] = hz * m.z;
-                    nd = make_float4(hx, hy, hz, 1.0f);
-                    pd.w = 1.0f;
-                }
-            } else if ((flags & DELORA_LOSS_PO2PO) && !src_has && !tgt_has) {            // :83-99, :168-179
-                acc[24] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                acc[25] = 1.0f;
-                acc[26] = dx; acc[27] = dy; acc[28] = dz;
-                acc[29] = dx * p.x; acc[30] = dx * p.y; acc[31] = dx * p.z;
-                acc[32] = dy * p.x; acc[33] = dy * p.y; acc[34] = dy * p.z;
-                acc[35] = dz * p.x; acc[36] = dz * p.y; acc[37] = dz * p.z;
-                pd = make_float4(dx, dy, dz, 2.0f);
-            }
+            paired = true;
+            tq = __ldg(tp + best.pos);
+            tnq = __ldg(tn + best.pos);
         }
+    }
+    // the accumulators only come alive after the search (keeps the search loop's register set small)
+    float acc[kIcpAcc];
+#pragma unroll
+    for (int k = 0; k < kIcpAcc; ++k) acc[k] = 0.0f;
+    if (active) {
+        float4 pd = make_float4(0.f, 0.f, 0.f, 0.f), nd = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (paired) accumulate_pair(flags, p, m, sx, sy, sz, nsx, nsy, nsz, tq, tnq, acc, pd, nd);
         if (point_dir) point_dir[(size_t)b * src_stride + i] = pd;
         if (normal_dir) normal_dir[(size_t)b * src_stride + i] = nd;
     }
-
-    // block reduction: shuffle tree per warp, then 8 warp rows summed in a fixed order
-    __shared__ float red[kIcpThreads / 32][DELORA_ICP_PARTIAL];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 38; ++k) {
-        const float s = warp_sum(acc[k]);
-        if (lane == 0) red[w][k] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < DELORA_ICP_PARTIAL) {
-        float s = 0.0f;
-        if (threadIdx.x < 38) {
-#pragma unroll
-            for (int j = 0; j < kIcpThreads / 32; ++j) s += red[j][threadIdx.x];
-        }
-        partials[((size_t)b * gridDim.x + blockIdx.x) * DELORA_ICP_PARTIAL + threadIdx.x] = s;
-    }
+    const int warp_row = (blockIdx.x * kIcpThreads + threadIdx.x) >> 5;
+    if (warp_row < rows_per_pair)
+        write_warp_partials(acc, partial_rows + ((size_t)b * rows_per_pair + warp_row) * DELORA_ICP_PARTIAL);
 }
 
-// One block per pair: fixed-order sum of the block partials, then the means and the gradient.
-__global__ void __launch_bounds__(64)
-icp_finalize_kernel(const float* __restrict__ partials, int nblocks, float lambda_po2pl, uint32_t flags,
-                    float* __restrict__ losses, float* __restrict__ grad_T) {
+// Column sums of the per-warp partial rows: one block per (column, pair), fixed-order tree in fp64
+// (deterministic); the last block of a pair to finish turns the 40 sums into the means and the
+// 3x4 gradient and re-arms the pair's counter.
+__global__ void __launch_bounds__(256)
+icp_finalize_kernel(const float* __restrict__ rows, int rows_per_pair, float* __restrict__ colsum,
+                    int* __restrict__ counter, float lambda_po2pl, float* __restrict__ losses,
+                    float* __restrict__ grad_T) {
+    __shared__ double red[256];
     __shared__ float s[DELORA_ICP_PARTIAL];
-    const int b = blockIdx.x;
-    if (threadIdx.x < DELORA_ICP_PARTIAL) {
-        // two interleaved double accumulators: deterministic, and keeps 1e-7-level accuracy over 500+ blocks
-        double a0 = 0.0, a1 = 0.0;
-        const float* __restrict__ p = partials + (size_t)b * nblocks * DELORA_ICP_PARTIAL + threadIdx.x;
-        int j = 0;
-        for (; j + 1 < nblocks; j += 2) {
-            a0 += (double)p[(size_t)j * DELORA_ICP_PARTIAL];
-            a1 += (double)p[(size_t)(j + 1) * DELORA_ICP_PARTIAL];
-        }
-        if (j < nblocks) a0 += (double)p[(size_t)j * DELORA_ICP_PARTIAL];
-        s[threadIdx.x] = (float)(a0 + a1);
+    __shared__ int is_last;
+    const int c = blockIdx.x, b = blockIdx.y;
+    const float* __restrict__ p = rows + (size_t)b * rows_per_pair * DELORA_ICP_PARTIAL + c;
+    double a = 0.0;
+    for (int r = threadIdx.x; r < rows_per_pair; r += 256) a += (double)p[(size_t)r * DELORA_ICP_PARTIAL];
+    red[threadIdx.x] = a;
+    __syncthreads();
+#pragma unroll
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        colsum[(size_t)b * DELORA_ICP_PARTIAL + c] = (float)red[0];
+        __threadfence();
+        const int prev = atomicAdd(counter + b, 1);
+        is_last = (prev == DELORA_ICP_PARTIAL - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < DELORA_ICP_PARTIAL) s[threadIdx.x] = __ldcg(colsum + (size_t)b * DELORA_ICP_PARTIAL + threadIdx.x);
+    if (threadIdx.x == 0) counter[b] = 0;
     __syncthreads();
     const float M = s[2], Mp = s[25];
     const float inv_m = M > 0.0f ? 1.0f / M : 0.0f;              // torch's mean over an empty set is NaN; we return 0
@@ -281,6 +211,16 @@ icp_finalize_kernel(const float* __restrict__ partials, int nblocks, float lambd
         }
         grad_T[(size_t)b * 12 + threadIdx.x] = gval;
     }
+}
+
+int launch_icp_finalize(float* scratch, int B, int rows, float lambda_po2pl, uint32_t flags, float* losses,
+                        float* grad_T, cudaStream_t st) {
+    (void)flags;
+    const IcpScratch sc = icp_scratch(scratch, B, rows);
+    dim3 grid(DELORA_ICP_PARTIAL, B);
+    icp_finalize_kernel<<<grid, 256, 0, st>>>(sc.rows, rows, sc.colsum, sc.counter, lambda_po2pl, losses, grad_T);
+    DELORA_CHECK_LAUNCH("icp_finalize_kernel");
+    return 0;
 }
 
 // Per-point gradients for the drop-in autograd path (ICPLosses.forward takes already-transformed
@@ -365,7 +305,11 @@ __global__ void quat_to_T_bwd_kernel(const float* __restrict__ quat, const float
 
 using namespace delora;
 
-extern "C" int delora_icp_blocks(int src_stride) { return (src_stride + kIcpThreads - 1) / kIcpThreads; }
+extern "C" int delora_icp_partial_rows(int src_stride) { return (src_stride + 31) / 32; }
+
+extern "C" int64_t delora_icp_scratch_floats(int B, int src_stride) {
+    return (int64_t)B * delora_icp_partial_rows(src_stride) * DELORA_ICP_PARTIAL + (int64_t)B * DELORA_ICP_PARTIAL + B;
+}
 
 extern "C" int delora_icp_fwd_bwd(const delora_f4* src_pts4, const delora_f4* src_nrm4, const int32_t* n_src,
                                   int src_stride, const float* T, const delora_f4* tgt_pts4,
@@ -379,24 +323,23 @@ extern "C" int delora_icp_fwd_bwd(const delora_f4* src_pts4, const delora_f4* sr
     DELORA_CHECK_ARG(B > 0 && B <= 65535 && src_stride > 0 && tgt_stride > 0 && H > 0 && W > 0,
                      "delora_icp_fwd_bwd: bad shape");
     const GridParams g = make_grid(H, W, hfov0, hfov1, vfov0, vfov1, 0);
-    const int nblocks = delora_icp_blocks(src_stride);
-    dim3 grid(nblocks, B);
+    const int rows = delora_icp_partial_rows(src_stride);
+    const IcpScratch sc = icp_scratch(partials, B, rows);
+    dim3 grid((src_stride + kIcpThreads - 1) / kIcpThreads, B);
     cudaStream_t st = (cudaStream_t)stream;
     if (T) {
         icp_kernel<true><<<grid, kIcpThreads, 0, st>>>(
             (const float4*)src_pts4, (const float4*)src_nrm4, n_src, src_stride, T, (const float4*)tgt_pts4,
             (const float4*)tgt_nrm4, cell_start, tgt_stride, g, flags, nn_index, (float4*)point_dir,
-            (float4*)normal_dir, partials);
+            (float4*)normal_dir, sc.rows, rows);
     } else {
         icp_kernel<false><<<grid, kIcpThreads, 0, st>>>(
             (const float4*)src_pts4, (const float4*)src_nrm4, n_src, src_stride, T, (const float4*)tgt_pts4,
             (const float4*)tgt_nrm4, cell_start, tgt_stride, g, flags, nn_index, (float4*)point_dir,
-            (float4*)normal_dir, partials);
+            (float4*)normal_dir, sc.rows, rows);
     }
     DELORA_CHECK_LAUNCH("icp_kernel");
-    icp_finalize_kernel<<<B, 64, 0, st>>>(partials, nblocks, lambda_po2pl, flags, losses, grad_T);
-    DELORA_CHECK_LAUNCH("icp_finalize_kernel");
-    return 0;
+    return launch_icp_finalize(partials, B, rows, lambda_po2pl, flags, losses, grad_T, st);
 }
 
 extern "C" int delora_icp_point_grads(const delora_f4* point_dir, const delora_f4* normal_dir,

@@ -1,0 +1,224 @@
+// Fused SE(3) transform + exact NN + ICP losses fwd/bwd on DENSE range-image grids (sm_100a).
+//
+// Same contract as icp.cu (reference: src/deploy/deployer.py:181-189, src/losses/icp_losses.py:28-240),
+// specialised for the case the training step actually has: source and target are the valid pixels
+// of two projected H x W range images, i.e. at most one point per spherical cell.  Points and
+// normals live as float4 per pixel ((x, y, z, pixel id) / (nx, ny, nz, has_normal); empty pixels
+// are (+inf, +inf, +inf, -1)), written by the normals kernel, so no list compaction and no
+// CSR index are needed and a window of cells is a fixed-stride walk over one array.
+//
+// One thread per SOURCE PIXEL; a warp = 32 adjacent pixels.  The search window is described by
+// warp-uniform extents (rows down/up, columns left/right of every lane's own centre cell) and
+// grows one strip at a time while ANY lane's exactness guard still fails, on the side the first
+// failing lane needs.  Control flow is warp-uniform (no divergence), adjacent lanes read adjacent
+// cells (coalesced, L1-resident), and the guard is the same proof as in icp.cu: all unsearched
+// targets lie beyond a border half-plane (azimuth) or cone (elevation) of the lane's window.
+#include "icp_common.cuh"
+
+namespace delora {
+
+constexpr int kDenseThreads = 128;
+
+__device__ __forceinline__ int wrap_col(int c, int W) {
+    c += (c < 0) ? W : 0;
+    c -= (c >= W) ? W : 0;
+    return c;
+}
+
+// lower bound of the distance from the source point to everything beyond a window border that is
+// `dpx` pixels (of `rad_per_px` radians) away; `radius` is |p| (elevation cones) or |p_xy| (azimuth planes)
+__device__ __forceinline__ float border_bound(float dpx, float rad_per_px, float radius) {
+    const float d = fminf(fmaxf(dpx * rad_per_px, 0.0f), kHalfPiF);
+    return radius * __sinf(d);
+}
+
+// Branch-free running (smallest, second smallest) fp32 squared distance + index of the smallest.
+// The whole search runs on this; float64 is only consulted afterwards if the two smallest are
+// within kNNBand of each other (nn_exact_rescan).
+struct NN2 {
+    float m1, m2;
+    int j1;
+};
+
+__device__ __forceinline__ void nn2_eval(const float4 t, int j, float sx, float sy, float sz, NN2& s) {
+    const float dx = sx - t.x, dy = sy - t.y, dz = sz - t.z;
+    const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const bool lt = d2f < s.m1;
+    s.m2 = lt ? s.m1 : fminf(s.m2, d2f);
+    s.j1 = lt ? j : s.j1;
+    s.m1 = lt ? d2f : s.m1;
+}
+
+__device__ __forceinline__ float4 inf4() {
+    const float inf = __int_as_float(0x7f800000);
+    return make_float4(inf, inf, inf, __int_as_float(-1));
+}
+
+// Rare path: two candidates within the fp32 ambiguity band.  Re-rank every candidate of the
+// final window whose fp32 distance is inside the band in float64 (lowest pixel id on exact ties).
+__device__ __noinline__ int nn_exact_rescan(const float4* __restrict__ tg, int H, int W, int rc, int cc, int e_dn,
+                                            int e_up, int e_lf, int e_rt, float sx, float sy, float sz,
+                                            float thresh) {
+    double best = 1.0e300;
+    int bj = -1;
+    for (int dr = -e_dn; dr <= e_up; ++dr) {
+        const int row = rc + dr;
+        if (row < 0 || row >= H) continue;
+        for (int dc = -e_lf; dc <= e_rt; ++dc) {
+            const int j = row * W + wrap_col(cc + dc, W);
+            const float4 t = __ldg(tg + j);
+            const float dx = sx - t.x, dy = sy - t.y, dz = sz - t.z;
+            const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (d2f <= thresh) {
+                const double d2 = nn_d2_exact(sx, sy, sz, t.x, t.y, t.z);
+                if (d2 < best || (d2 == best && j < bj)) { best = d2; bj = j; }
+            }
+        }
+    }
+    return bj;
+}
+
+template <bool PO2PO>
+__global__ void __launch_bounds__(kDenseThreads, 8)
+icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__ src_ngrid,
+                 const float* __restrict__ T, const float4* __restrict__ tgt_grid,
+                 const float4* __restrict__ tgt_ngrid, GridParams g, uint32_t flags,
+                 float* __restrict__ partial_rows, int rows_per_pair) {
+    const int b = blockIdx.y;
+    const int H = g.H, W = g.W, HW = H * W;
+    const float4* __restrict__ tg = tgt_grid + (size_t)b * HW;
+    const float4* __restrict__ tn = tgt_ngrid + (size_t)b * HW;
+    const int i = blockIdx.x * kDenseThreads + threadIdx.x;
+    const int warp_in_pair = i >> 5;
+    constexpr float kInf = 3.0e38f;
+    constexpr float kSlack = 2e-3f;     // px; covers the fp32 error of the cell binning
+
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), m = p;
+    bool active = false;
+    if (i < HW) {
+        p = __ldg(src_grid + (size_t)b * HW + i);
+        active = __float_as_int(p.w) >= 0;
+        if (active) m = __ldg(src_ngrid + (size_t)b * HW + i);
+    }
+    float sx = 0.f, sy = 0.f, sz = 0.f, nsx = 0.f, nsy = 0.f, nsz = 0.f;
+    if (active) {
+        const Rigid rt = load_rigid(T + (size_t)b * 12);
+        apply_rigid(rt, p, m, sx, sy, sz, nsx, nsy, nsz);
+    }
+    int best_j = -1;
+    if (__ballot_sync(0xffffffffu, active) != 0u) {
+        float us = 0.f, vs = 0.f;
+        pixel_coords(g, sx, sy, sz, us, vs);
+        if (!(us == us)) us = 0.0f;
+        if (!(vs == vs)) vs = 0.0f;
+        const float rxy = sqrtf(fmaf(sx, sx, sy * sy));
+        const float r = sqrtf(fmaf(sz, sz, fmaf(sx, sx, sy * sy)));
+        const int cc = (int)fminf(fmaxf(rintf(us), 0.0f), g.wm1);
+        const int rc = (int)fminf(fmaxf(rintf(vs), 0.0f), g.hm1);
+        // distance (px) from the source direction to the four borders of its own centre cell
+        const float f_dn = (vs - (float)rc) + 0.5f - kSlack, f_up = ((float)rc - vs) + 0.5f - kSlack;
+        const float f_lf = (us - (float)cc) + 0.5f - kSlack, f_rt = ((float)cc - us) + 0.5f - kSlack;
+
+        NN2 nn;
+        nn.m1 = kInf; nn.m2 = kInf; nn.j1 = -1;
+        // warp-uniform window extents around every lane's own (rc, cc); the 3 x 5 start window is
+        // fully unrolled: 15 independent loads in flight
+        int e_dn = 1, e_up = 1, e_lf = 2, e_rt = 2;
+        if (H >= 3 && W >= 5) {
+#pragma unroll
+            for (int dr = -1; dr <= 1; ++dr) {
+                const int row = rc + dr;
+                const bool rok = active && row >= 0 && row < H;
+#pragma unroll
+                for (int dc = -2; dc <= 2; ++dc) {
+                    const int j = row * W + wrap_col(cc + dc, W);
+                    nn2_eval(rok ? __ldg(tg + j) : inf4(), j, sx, sy, sz, nn);
+                }
+            }
+        } else {
+            e_dn = e_up = e_lf = e_rt = 0;
+            if (active) nn2_eval(__ldg(tg + rc * W + cc), rc * W + cc, sx, sy, sz, nn);
+        }
+        while (true) {
+            const float b_dn = (rc - e_dn > 0) ? border_bound(f_dn + (float)e_dn, g.dv_rad, r) : kInf;
+            const float b_up = (rc + e_up < H - 1) ? border_bound(f_up + (float)e_up, g.dv_rad, r) : kInf;
+            const bool full_w = (e_lf + e_rt + 1 >= W);
+            const float b_lf = full_w ? kInf : border_bound(f_lf + (float)e_lf, g.du_rad, rxy);
+            const float b_rt = full_w ? kInf : border_bound(f_rt + (float)e_rt, g.du_rad, rxy);
+            const float bmin = fminf(fminf(b_dn, b_up), fminf(b_lf, b_rt));
+            const bool done = !active || bmin >= kInf ||
+                              (nn.j1 >= 0 && sqrtf(nn.m1) * 1.00001f <= bmin * 0.9995f);
+            const unsigned failing = __ballot_sync(0xffffffffu, !done);
+            if (failing == 0u) break;
+            const int my_side = (bmin == b_dn) ? 0 : (bmin == b_up) ? 1 : (bmin == b_lf) ? 2 : 3;
+            const int side = __shfl_sync(0xffffffffu, my_side, __ffs(failing) - 1);
+            if (side < 2) {
+                const int row = (side == 0) ? rc - (++e_dn) : rc + (++e_up);
+                const bool rok = active && row >= 0 && row < H;
+                const int n = e_lf + e_rt + 1;
+#pragma unroll 4
+                for (int k = 0; k < n; ++k) {
+                    const int j = row * W + wrap_col(cc - e_lf + k, W);
+                    nn2_eval(rok ? __ldg(tg + j) : inf4(), j, sx, sy, sz, nn);
+                }
+            } else {
+                const int step = min(2, W - (e_lf + e_rt + 1));
+                const int c0 = wrap_col((side == 2) ? cc - e_lf - 1 : cc + e_rt + 1, W);
+                const int c1 = wrap_col((side == 2) ? cc - e_lf - 2 : cc + e_rt + 2, W);
+                const int n = e_dn + e_up + 1;
+#pragma unroll 2
+                for (int k = 0; k < n; ++k) {
+                    const int row = rc - e_dn + k;
+                    const bool rok = active && row >= 0 && row < H;
+                    nn2_eval(rok ? __ldg(tg + row * W + c0) : inf4(), row * W + c0, sx, sy, sz, nn);
+                    if (step == 2) nn2_eval(rok ? __ldg(tg + row * W + c1) : inf4(), row * W + c1, sx, sy, sz, nn);
+                }
+                if (side == 2) e_lf += step; else e_rt += step;
+            }
+        }
+        best_j = nn.j1;
+        if (active && best_j >= 0 && nn.m2 <= nn.m1 * (1.0f + kNNBand))
+            best_j = nn_exact_rescan(tg, H, W, rc, cc, e_dn, e_up, e_lf, e_rt, sx, sy, sz, nn.m1 * (1.0f + kNNBand));
+    }
+    float acc[kIcpAcc];
+#pragma unroll
+    for (int k = 0; k < kIcpAcc; ++k) acc[k] = 0.0f;
+    if (active && best_j >= 0) {
+        float4 pd, nd;
+        accumulate_pair(PO2PO ? flags : (flags & ~DELORA_LOSS_PO2PO), p, m, sx, sy, sz, nsx, nsy, nsz,
+                        __ldg(tg + best_j), __ldg(tn + best_j), acc, pd, nd);
+    }
+    if (warp_in_pair < rows_per_pair)
+        write_warp_partials<(PO2PO ? kIcpAcc : 24)>(
+            acc, partial_rows + ((size_t)b * rows_per_pair + warp_in_pair) * DELORA_ICP_PARTIAL);
+}
+
+}  // namespace delora
+
+using namespace delora;
+
+extern "C" int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_f4* src_ngrid, const float* T,
+                                        const delora_f4* tgt_grid, const delora_f4* tgt_ngrid, int B, int H, int W,
+                                        double hfov0, double hfov1, double vfov0, double vfov1, float lambda_po2pl,
+                                        uint32_t flags, float* losses, float* grad_T, float* scratch, void* stream) {
+    DELORA_CHECK_ARG(src_grid && src_ngrid && T && tgt_grid && tgt_ngrid && losses && grad_T && scratch,
+                     "delora_icp_dense_fwd_bwd: null pointer");
+    DELORA_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0, "delora_icp_dense_fwd_bwd: bad shape");
+    const GridParams g = make_grid(H, W, hfov0, hfov1, vfov0, vfov1, 0);
+    const int HW = H * W;
+    const int rows = (HW + 31) / 32;                  // one partial row per warp of 32 source pixels
+    const IcpScratch sc = icp_scratch(scratch, B, rows);
+    dim3 grid((HW + kDenseThreads - 1) / kDenseThreads, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (flags & DELORA_LOSS_PO2PO) {
+        icp_dense_kernel<true><<<grid, kDenseThreads, 0, st>>>((const float4*)src_grid, (const float4*)src_ngrid, T,
+                                                               (const float4*)tgt_grid, (const float4*)tgt_ngrid, g,
+                                                               flags, sc.rows, rows);
+    } else {
+        icp_dense_kernel<false><<<grid, kDenseThreads, 0, st>>>((const float4*)src_grid, (const float4*)src_ngrid, T,
+                                                                (const float4*)tgt_grid, (const float4*)tgt_ngrid, g,
+                                                                flags, sc.rows, rows);
+    }
+    DELORA_CHECK_LAUNCH("icp_dense_kernel");
+    return launch_icp_finalize(scratch, B, rows, lambda_po2pl, flags, losses, grad_T, st);
+}

@@ -71,7 +71,8 @@ __device__ __forceinline__ void smallest_eigenvector(Sym3 m, float& nx, float& n
 template <int A_, int B_>
 __global__ void __launch_bounds__(kNormTW * kNormTH)
 normals_kernel(const float* __restrict__ image, int C_img, int H, int W, int a_rt, int b_rt,
-               float eps_range, int min_nb, float* __restrict__ normals) {
+               float eps_range, int min_nb, float* __restrict__ normals, float4* __restrict__ pts_grid,
+               float4* __restrict__ nrm_grid) {
     extern __shared__ float4 tile[];
     const int a = (A_ >= 0) ? A_ : a_rt;
     const int b = (B_ >= 0) ? B_ : b_rt;
@@ -99,7 +100,8 @@ normals_kernel(const float* __restrict__ image, int C_img, int H, int W, int a_r
     if (u >= W || v >= H) return;
     const float4 c = tile[(lv + a) * tw + (lu + b)];
     float nx = 0.f, ny = 0.f, nz = 0.f;
-    if (c.x != 0.0f && c.y != 0.0f && c.z != 0.0f) {                  // normal_computation.py:35
+    const bool valid = c.x != 0.0f && c.y != 0.0f && c.z != 0.0f;     // normal_computation.py:35
+    if (valid) {
         const int ntaps = (2 * a + 1) * (2 * b + 1);
         // clamped window in tile coordinates
         float sx = 0.f, sy = 0.f, sz = 0.f;
@@ -147,8 +149,19 @@ normals_kernel(const float* __restrict__ image, int C_img, int H, int W, int a_r
             if (nx * c.x + ny * c.y + nz * c.z > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }   // :79-81
         }
     }
-    float* __restrict__ out = normals + (size_t)bi * 3 * HW + (size_t)v * W + u;
-    out[0] = nx; out[HW] = ny; out[2 * HW] = nz;
+    const size_t pix = (size_t)v * W + u;
+    if (normals) {
+        float* __restrict__ out = normals + (size_t)bi * 3 * HW + pix;
+        out[0] = nx; out[HW] = ny; out[2 * HW] = nz;
+    }
+    if (pts_grid) {
+        // dense float4 grids for the ICP kernel: one valid point per cell, empty cells at +inf
+        const float inf = __int_as_float(0x7f800000);
+        pts_grid[(size_t)bi * HW + pix] = valid ? make_float4(c.x, c.y, c.z, __int_as_float((int)pix))
+                                                : make_float4(inf, inf, inf, __int_as_float(-1));
+        const bool has = (nx != 0.0f) | (ny != 0.0f) | (nz != 0.0f);                     // icp_losses.py:48-52
+        nrm_grid[(size_t)bi * HW + pix] = make_float4(nx, ny, nz, has ? 1.0f : 0.0f);
+    }
 }
 
 }  // namespace delora
@@ -156,8 +169,10 @@ normals_kernel(const float* __restrict__ image, int C_img, int H, int W, int a_r
 using namespace delora;
 
 extern "C" int delora_normals_fwd(const float* image, int B, int C_img, int H, int W, int nb_h, int nb_w,
-                                  float epsilon_range, int min_neighbors, float* normals, void* stream) {
-    DELORA_CHECK_ARG(image && normals, "delora_normals_fwd: null pointer");
+                                  float epsilon_range, int min_neighbors, float* normals, delora_f4* pts_grid,
+                                  delora_f4* nrm_grid, void* stream) {
+    DELORA_CHECK_ARG(image && (normals || pts_grid), "delora_normals_fwd: null pointer");
+    DELORA_CHECK_ARG((pts_grid == nullptr) == (nrm_grid == nullptr), "delora_normals_fwd: pts_grid and nrm_grid go together");
     DELORA_CHECK_ARG(B > 0 && B <= 65535 && C_img >= 3 && H > 0 && W > 0, "delora_normals_fwd: bad shape");
     const int a = nb_h / 2, b = nb_w / 2;                              // int(side/2): normal_computation.py:97-98
     DELORA_CHECK_ARG(a >= 0 && b >= 0 && a <= 16 && b <= 32, "delora_normals_fwd: neighbourhood %dx%d unsupported",
@@ -167,7 +182,8 @@ extern "C" int delora_normals_fwd(const float* image, int B, int C_img, int H, i
     cudaStream_t st = (cudaStream_t)stream;
     if (a == 3 && b == 5) {
         normals_kernel<3, 5><<<grid, kNormTW * kNormTH, smem, st>>>(image, C_img, H, W, a, b, epsilon_range,
-                                                                    min_neighbors, normals);
+                                                                    min_neighbors, normals, (float4*)pts_grid,
+                                                                    (float4*)nrm_grid);
     } else {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(normals_kernel<-1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -175,7 +191,8 @@ extern "C" int delora_normals_fwd(const float* image, int B, int C_img, int H, i
             DELORA_CHECK_ARG(e == cudaSuccess, "delora_normals_fwd: smem opt-in failed: %s", cudaGetErrorString(e));
         }
         normals_kernel<-1, -1><<<grid, kNormTW * kNormTH, smem, st>>>(image, C_img, H, W, a, b, epsilon_range,
-                                                                      min_neighbors, normals);
+                                                                      min_neighbors, normals, (float4*)pts_grid,
+                                                                      (float4*)nrm_grid);
     }
     DELORA_CHECK_LAUNCH("normals_kernel");
     return 0;

@@ -5,9 +5,8 @@
 // (:63), walks it serially keeping the first point that lands in each pixel (:34-43, numba on
 // the CPU) and scatters the survivors (:98-103).  "First in range order" == "minimum range",
 // so here every point does one 64-bit atomicMin of (range_bits << 32 | point_index) on its
-// pixel (equal ranges: lowest index wins == a stable sort), warp-aggregated so that points of
-// one warp that share a pixel issue a single atomic; a second pass resolves the winners into
-// the image and the pixel -> point index map and re-arms the key buffer.
+// pixel (equal ranges: lowest index wins == a stable sort); a second pass resolves the winners
+// into the image and the pixel -> point index map and re-arms the key buffer.
 //
 // HBM/L2 traffic per scan: read 12 N (xyz) [+ 8 HW key RMW in L2] ; write 4 (C+1) HW + 4 HW.
 #include "common.cuh"
@@ -46,14 +45,14 @@ project_scatter_kernel(const float* __restrict__ points, const int32_t* __restri
         pixel_coords(g, x[i], y[i], z[i], u, v);
         const float ru = rintf(u), rv = rintf(v);            // torch.round: half to even (:74-77)
         const bool inside = (idx < n) && (ru <= g.wm1) && (ru >= 0.0f) && (rv <= g.hm1) && (rv >= 0.0f);
-        const int pix = inside ? ((int)rv * g.W + (int)ru) : (-1 - (int)(threadIdx.x & 31));
-        const unsigned rbits = __float_as_uint(range3(x[i], y[i], z[i]));
-        // warp aggregation: lanes that hit the same pixel elect the (min range, min index) lane
-        const unsigned peers = __match_any_sync(0xffffffffu, pix);
-        const unsigned rmin = __reduce_min_sync(peers, rbits);
-        const unsigned imin = __reduce_min_sync(peers, rbits == rmin ? (unsigned)idx : 0xffffffffu);
-        if (inside && rbits == rmin && (unsigned)idx == imin) {
-            atomicMin(kb + pix, ((unsigned long long)rbits << 32) | (unsigned)idx);
+        if (inside) {
+            const unsigned rbits = __float_as_uint(range3(x[i], y[i], z[i]));
+            // One 64-bit atomicMin (a fire-and-forget RED at L2) per in-FOV point.  A match.any /
+            // redux.min warp aggregation was measured to be 2x SLOWER here: redux with per-group
+            // masks serialises once per distinct pixel (~28 groups per warp at W = 2048; ncu:
+            // CREDUX.MIN executed 27.9x per warp-instruction, >50 % of all issued instructions),
+            // while 2 M atomics per step are far below the L2 atomic rate (profiles/r01_*.md).
+            atomicMin(kb + (int)rv * g.W + (int)ru, ((unsigned long long)rbits << 32) | (unsigned)idx);
         }
     }
 }

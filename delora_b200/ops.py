@@ -75,15 +75,21 @@ def sort_by_range(rng, n_points):
     return order
 
 
-def normals(image, neighborhood=(7, 11), epsilon_range=0.5, min_neighbors=10):
-    """image [B,C,H,W] -> normals [B,3,H,W] (src/preprocessing/normal_computation.py:89-122)."""
+def normals(image, neighborhood=(7, 11), epsilon_range=0.5, min_neighbors=10, grids=False):
+    """image [B,C,H,W] -> normals [B,3,H,W] (src/preprocessing/normal_computation.py:89-122).
+    grids=True additionally returns the dense float4 grids (pts_grid, nrm_grid) [B,HW,4]."""
     b, c, h, w = image.shape
     out = torch.empty((b, 3, h, w), dtype=torch.float32, device=image.device)
+    pg = ng = None
+    if grids:
+        pg = torch.empty((b, h * w, 4), dtype=torch.float32, device=image.device)
+        ng = torch.empty((b, h * w, 4), dtype=torch.float32, device=image.device)
     L = _lib.lib()
     _lib.check(L.delora_normals_fwd(_req(image, torch.float32, "image"), b, c, h, w, int(neighborhood[0]),
                                     int(neighborhood[1]), float(epsilon_range), int(min_neighbors),
-                                    out.data_ptr(), _stream()), "delora_normals_fwd")
-    return out
+                                    out.data_ptr(), pg.data_ptr() if grids else None,
+                                    ng.data_ptr() if grids else None, _stream()), "delora_normals_fwd")
+    return (out, pg, ng) if grids else out
 
 
 def lists_from_images(image, normals_img):
@@ -138,7 +144,7 @@ def pack_lists(pts, nrm, n):
 
 
 def icp_fwd_bwd(src_pts4, src_nrm4, n_src, transform, tgt_pts4, tgt_nrm4, cell_start, h, w, hfov, vfov,
-                lambda_po2pl=1.0, flags=LOSS_PO2PL | LOSS_PL2PL, pointwise=False, partials=None):
+                lambda_po2pl=1.0, flags=LOSS_PO2PL | LOSS_PL2PL, pointwise=False, scratch=None):
     """Fused transform + exact NN + losses + gradient.  transform: [B,12] (3x4 row-major) or None.
     -> losses [B,8], grad_T [B,12], (nn_index [B,Ns] int32, point_dir, normal_dir [B,Ns,4]) or Nones."""
     b, ns, _ = src_pts4.shape
@@ -147,8 +153,8 @@ def icp_fwd_bwd(src_pts4, src_nrm4, n_src, transform, tgt_pts4, tgt_nrm4, cell_s
     L = _lib.lib()
     losses = torch.empty((b, LOSS_ROW), dtype=torch.float32, device=dev)
     grad_t = torch.empty((b, 12), dtype=torch.float32, device=dev)
-    if partials is None:
-        partials = torch.empty((b * L.delora_icp_blocks(ns) * ICP_PARTIAL,), dtype=torch.float32, device=dev)
+    if scratch is None:
+        scratch = icp_scratch(b, ns, dev)
     nn_index = point_dir = normal_dir = None
     if pointwise:
         nn_index = torch.empty((b, ns), dtype=torch.int32, device=dev)
@@ -163,8 +169,33 @@ def icp_fwd_bwd(src_pts4, src_nrm4, n_src, transform, tgt_pts4, tgt_nrm4, cell_s
         float(hfov[0]), float(hfov[1]), float(vfov[0]), float(vfov[1]), float(lambda_po2pl), int(flags),
         losses.data_ptr(), grad_t.data_ptr(),
         nn_index.data_ptr() if pointwise else None, point_dir.data_ptr() if pointwise else None,
-        normal_dir.data_ptr() if pointwise else None, partials.data_ptr(), _stream()), "delora_icp_fwd_bwd")
+        normal_dir.data_ptr() if pointwise else None, scratch.data_ptr(), _stream()), "delora_icp_fwd_bwd")
     return losses, grad_t, nn_index, point_dir, normal_dir
+
+
+def icp_scratch(b, src_stride, device):
+    """Zero-initialised scratch for the ICP kernels (they leave its counters at zero)."""
+    return torch.zeros((int(_lib.lib().delora_icp_scratch_floats(b, src_stride)),), dtype=torch.float32,
+                       device=device)
+
+
+def icp_dense_fwd_bwd(src_grid, src_ngrid, transform, tgt_grid, tgt_ngrid, h, w, hfov, vfov, lambda_po2pl=1.0,
+                      flags=LOSS_PO2PL | LOSS_PL2PL, scratch=None):
+    """Dense-grid variant: grids [B,HW,4] from normals(grids=True); transform [B,12]."""
+    b = src_grid.shape[0]
+    dev = src_grid.device
+    losses = torch.empty((b, LOSS_ROW), dtype=torch.float32, device=dev)
+    grad_t = torch.empty((b, 12), dtype=torch.float32, device=dev)
+    if scratch is None:
+        scratch = icp_scratch(b, h * w, dev)
+    L = _lib.lib()
+    _lib.check(L.delora_icp_dense_fwd_bwd(
+        _req(src_grid, torch.float32, "src_grid"), _req(src_ngrid, torch.float32, "src_ngrid"),
+        _req(transform, torch.float32, "transform"), _req(tgt_grid, torch.float32, "tgt_grid"),
+        _req(tgt_ngrid, torch.float32, "tgt_ngrid"), b, h, w, float(hfov[0]), float(hfov[1]), float(vfov[0]),
+        float(vfov[1]), float(lambda_po2pl), int(flags), losses.data_ptr(), grad_t.data_ptr(),
+        scratch.data_ptr(), _stream()), "delora_icp_dense_fwd_bwd")
+    return losses, grad_t
 
 
 def icp_point_grads(point_dir, normal_dir, n_src, losses, upstream):

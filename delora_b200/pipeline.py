@@ -31,18 +31,14 @@ class ScanPairPipeline:
         self.keys = torch.full((b2, hw), -1, dtype=torch.int64, device=dev)
         self.image = torch.empty((b2, self.C + 1, self.H, self.W), dtype=f32, device=dev)
         self.index_map = torch.empty((b2, self.H, self.W), dtype=i32, device=dev)
-        self.normals = torch.empty((b2, 3, self.H, self.W), dtype=f32, device=dev)
-        self.pts4 = torch.empty((b2, hw, 4), dtype=f32, device=dev)
-        self.nrm4 = torch.empty((b2, hw, 4), dtype=f32, device=dev)
-        self.cell_start = torch.empty((b2, hw + 1), dtype=i32, device=dev)
-        self.counts = torch.empty((b2,), dtype=i32, device=dev)
-        self.scan_scratch = torch.empty((b2 * self.L.delora_scan_blocks(hw),), dtype=i32, device=dev)
+        # dense float4 grids written by the normals kernel: (x,y,z,pixel id) / (nx,ny,nz,has_normal)
+        self.pts_grid = torch.empty((b2, hw, 4), dtype=f32, device=dev)
+        self.nrm_grid = torch.empty((b2, hw, 4), dtype=f32, device=dev)
         self.transform = torch.zeros((self.B, 12), dtype=f32, device=dev)
         self.losses = torch.empty((self.B, ops.LOSS_ROW), dtype=f32, device=dev)
         self.grad_T = torch.empty((self.B, 12), dtype=f32, device=dev)
-        self.partials = torch.empty((self.B * self.L.delora_icp_blocks(hw) * ops.ICP_PARTIAL,), dtype=f32,
-                                    device=dev)
-        self.launches_per_step = 2 + 1 + 2 + 2   # scatter+resolve, normals, count+emit, icp+finalize
+        self.icp_scratch = ops.icp_scratch(self.B, hw, dev)       # zeroed once; the kernels keep it armed
+        self.launches_per_step = 2 + 1 + 2   # scatter+resolve, normals(+grids), icp_dense+finalize
 
     def load(self, scans_1, scans_2, transforms):
         """Host-side staging helper for tests: lists of [3,N_i] tensors + [B,4,4] transforms."""
@@ -53,12 +49,12 @@ class ScanPairPipeline:
             self.n_points[self.B + i] = s2.shape[1]
         self.transform.copy_(transforms[:, :3, :].reshape(self.B, 12).to(self.device))
 
-    OPERATORS = ("projection", "normals", "lists", "icp")
+    OPERATORS = ("projection", "normals", "icp")
 
     def step(self, events=None):
         """Enqueue the whole hot path on the current stream; returns (losses [B,8], grad_T [B,12]).
-        `events`: optional list of 5 torch.cuda.Event (timing enabled) recorded before the first and
-        after each of the four operators, for per-kernel timing inside a measured region."""
+        `events`: optional list of 4 torch.cuda.Event (timing enabled) recorded before the first and
+        after each of the three operators, for per-kernel timing inside a measured region."""
         L, st = self.L, torch.cuda.current_stream().cuda_stream
         if events is not None:
             events[0].record()
@@ -70,25 +66,20 @@ class ScanPairPipeline:
         if events is not None:
             events[1].record()
         _lib.check(L.delora_normals_fwd(self.image.data_ptr(), b2, self.C + 1, H, W, self.nb[0], self.nb[1],
-                                        self.eps, self.min_nb, self.normals.data_ptr(), st), "delora_normals_fwd")
+                                        self.eps, self.min_nb, None, self.pts_grid.data_ptr(),
+                                        self.nrm_grid.data_ptr(), st), "delora_normals_fwd")
         if events is not None:
             events[2].record()
-        _lib.check(L.delora_lists_from_images(self.image.data_ptr(), self.normals.data_ptr(), b2, self.C + 1, H, W,
-                                              self.pts4.data_ptr(), self.nrm4.data_ptr(),
-                                              self.cell_start.data_ptr(), self.counts.data_ptr(),
-                                              self.scan_scratch.data_ptr(), st), "delora_lists_from_images")
-        if events is not None:
-            events[3].record()
         # source = scan_2 (second half), target = scan_1 (first half): deployer.py:294-307
         f4 = 16
-        _lib.check(L.delora_icp_fwd_bwd(self.pts4.data_ptr() + B * hw * f4, self.nrm4.data_ptr() + B * hw * f4,
-                                        self.counts.data_ptr() + B * 4, hw, self.transform.data_ptr(),
-                                        self.pts4.data_ptr(), self.nrm4.data_ptr(), self.cell_start.data_ptr(), hw,
-                                        B, H, W, hf[0], hf[1], vf[0], vf[1], self.lam, self.flags,
-                                        self.losses.data_ptr(), self.grad_T.data_ptr(), None, None, None,
-                                        self.partials.data_ptr(), st), "delora_icp_fwd_bwd")
+        _lib.check(L.delora_icp_dense_fwd_bwd(self.pts_grid.data_ptr() + B * hw * f4,
+                                              self.nrm_grid.data_ptr() + B * hw * f4, self.transform.data_ptr(),
+                                              self.pts_grid.data_ptr(), self.nrm_grid.data_ptr(), B, H, W,
+                                              hf[0], hf[1], vf[0], vf[1], self.lam, self.flags,
+                                              self.losses.data_ptr(), self.grad_T.data_ptr(),
+                                              self.icp_scratch.data_ptr(), st), "delora_icp_dense_fwd_bwd")
         if events is not None:
-            events[4].record()
+            events[3].record()
         return self.losses, self.grad_T
 
     def algorithmic_bytes(self, k_points=None):
@@ -100,6 +91,5 @@ class ScanPairPipeline:
         return {
             "projection": b2 * (4 * c * n + 4 * (c + 1) * hw + 4 * hw),          # read xyz, write image + index map
             "normals": b2 * (12 * hw + 12 * hw),                                   # read xyz image, write normals
-            "lists": b2 * (12 * hw + 12 * hw + 32 * k + 4 * hw),                   # read image+normals, write 2 float4 lists + CSR
             "icp": B * ((16 * hw + 12 * k + 4 * k) + (12 * k + 12 * k + 4 * k + 24 * k)),   # NN search + fused loss (K=M)
         }

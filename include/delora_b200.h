@@ -95,11 +95,15 @@ int delora_sort_by_range(const float* range, const int32_t* n_points, int B, int
  *
  * image      [B, C_img, H, W] fp32 (first three channels are x, y, z)
  * nb_h, nb_w neighbourhood side lengths (7, 11); patch = (2*(nb_h/2)+1) x (2*(nb_w/2)+1), edge-clamped
- * normals    [B, 3, H, W] fp32 out; 0 where the pixel is not valid (x!=0 & y!=0 & z!=0) or has
- *            fewer than `min_neighbors` range-gated neighbours.
+ * normals    [B, 3, H, W] fp32 out (may be NULL); 0 where the pixel is not valid (x!=0 & y!=0 & z!=0)
+ *            or has fewer than `min_neighbors` range-gated neighbours.
+ * pts_grid   [B, H*W] float4 out or NULL: (x, y, z, bits(pixel id)) of valid pixels, (+inf,+inf,+inf,-1) else
+ * nrm_grid   [B, H*W] float4 out or NULL: (nx, ny, nz, has_normal ? 1 : 0)   (both or neither)
+ *            -- the dense layout delora_icp_dense_fwd_bwd consumes (one point per spherical cell).
  */
 int delora_normals_fwd(const float* image, int B, int C_img, int H, int W, int nb_h, int nb_w,
-                       float epsilon_range, int min_neighbors, float* normals, void* stream);
+                       float epsilon_range, int min_neighbors, float* normals,
+                       delora_f4* pts_grid, delora_f4* nrm_grid, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Image -> lists (row-major order of the valid pixels), the layout the reference stores and
@@ -159,10 +163,13 @@ int delora_pack_lists(const float* pts, const float* nrm, const int32_t* n, int 
  *                   kept (normal, normal) pair; (s - t) with w = 2 for a po2po pair; w = 0 otherwise
  * normal_dir        [B, src_stride] float4 out or NULL: unscaled d(pl2pl)/d(source normal)
  *                   (delora_icp_point_grads turns the two into the reference-shaped gradients)
- * partials          fp32 scratch [B * delora_icp_blocks(src_stride) * DELORA_ICP_PARTIAL]
+ * scratch           fp32 [delora_icp_scratch_floats(B, src_stride)]: per-warp partial rows, column sums and
+ *                   B int32 completion counters.  Zero it ONCE after allocation; every call leaves the
+ *                   counters at zero again.
  * The NN is the exact float64 Euclidean nearest neighbour (lowest tag on exact ties).
  */
-int delora_icp_blocks(int src_stride);
+int     delora_icp_partial_rows(int src_stride);
+int64_t delora_icp_scratch_floats(int B, int src_stride);
 int delora_icp_fwd_bwd(const delora_f4* src_pts4, const delora_f4* src_nrm4, const int32_t* n_src,
                        int src_stride, const float* T,
                        const delora_f4* tgt_pts4, const delora_f4* tgt_nrm4, const int32_t* cell_start,
@@ -171,7 +178,19 @@ int delora_icp_fwd_bwd(const delora_f4* src_pts4, const delora_f4* src_nrm4, con
                        float lambda_po2pl, uint32_t flags,
                        float* losses, float* grad_T, int32_t* nn_index,
                        delora_f4* point_dir, delora_f4* normal_dir,
-                       float* partials, void* stream);
+                       float* scratch, void* stream);
+
+/* The same operator on dense range-image grids (the layout delora_normals_fwd writes): source =
+ * the valid pixels of `src_grid`, target = `tgt_grid`, at most one point per cell, so neither
+ * list compaction nor a CSR index is needed.  This is the training-step fast path
+ * (src/deploy/deployer.py:252-261 keeps exactly one point per pixel of both scans).
+ * src_grid/src_ngrid, tgt_grid/tgt_ngrid: [B, H*W] float4;  T: [B, 12];
+ * scratch: fp32 [delora_icp_scratch_floats(B, H*W)], zeroed once (see above). */
+int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_f4* src_ngrid, const float* T,
+                             const delora_f4* tgt_grid, const delora_f4* tgt_ngrid, int B, int H, int W,
+                             double hfov0, double hfov1, double vfov0, double vfov1,
+                             float lambda_po2pl, uint32_t flags, float* losses, float* grad_T,
+                             float* scratch, void* stream);
 
 /* Backward of ICPLosses.forward w.r.t. its two differentiable inputs, for callers that hand in
  * already-transformed clouds and let autograd continue (src/deploy/deployer.py:294-307 -> :341):

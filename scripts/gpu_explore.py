@@ -20,11 +20,9 @@ b2, H, hw = 2 * B, 64, 64 * W
 def t_proj():
     _lib.check(L.delora_project_fwd(pipe.points.data_ptr(), pipe.n_points.data_ptr(), b2, 3, pipe.N, H, W, hf[0], hf[1], vf[0], vf[1], 0, pipe.keys.data_ptr(), pipe.image.data_ptr(), pipe.index_map.data_ptr(), st), "p")
 def t_norm():
-    _lib.check(L.delora_normals_fwd(pipe.image.data_ptr(), b2, 4, H, W, 7, 11, 0.5, 10, pipe.normals.data_ptr(), st), "n")
-def t_lists():
-    _lib.check(L.delora_lists_from_images(pipe.image.data_ptr(), pipe.normals.data_ptr(), b2, 4, H, W, pipe.pts4.data_ptr(), pipe.nrm4.data_ptr(), pipe.cell_start.data_ptr(), pipe.counts.data_ptr(), pipe.scan_scratch.data_ptr(), st), "l")
+    _lib.check(L.delora_normals_fwd(pipe.image.data_ptr(), b2, 4, H, W, 7, 11, 0.5, 10, None, pipe.pts_grid.data_ptr(), pipe.nrm_grid.data_ptr(), st), "n")
 def t_icp():
-    _lib.check(L.delora_icp_fwd_bwd(pipe.pts4.data_ptr() + B * hw * 16, pipe.nrm4.data_ptr() + B * hw * 16, pipe.counts.data_ptr() + B * 4, hw, pipe.transform.data_ptr(), pipe.pts4.data_ptr(), pipe.nrm4.data_ptr(), pipe.cell_start.data_ptr(), hw, B, H, W, hf[0], hf[1], vf[0], vf[1], 1.0, 6, pipe.losses.data_ptr(), pipe.grad_T.data_ptr(), None, None, None, pipe.partials.data_ptr(), st), "i")
+    _lib.check(L.delora_icp_dense_fwd_bwd(pipe.pts_grid.data_ptr() + B * hw * 16, pipe.nrm_grid.data_ptr() + B * hw * 16, pipe.transform.data_ptr(), pipe.pts_grid.data_ptr(), pipe.nrm_grid.data_ptr(), B, H, W, hf[0], hf[1], vf[0], vf[1], 1.0, 6, pipe.losses.data_ptr(), pipe.grad_T.data_ptr(), pipe.icp_scratch.data_ptr(), st), "i")
 
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 def timeit(fn, name, iters=20):
@@ -42,9 +40,9 @@ def timeit(fn, name, iters=20):
 
 print(f"B={B} pairs, 64x{W}, N~{nmax}")
 tot = 0
-for fn, name in ((t_proj, "projection"), (t_norm, "normals"), (t_lists, "lists"), (t_icp, "icp")):
+for fn, name in ((t_proj, "projection"), (t_norm, "normals"), (t_icp, "icp_dense")):
     tot += timeit(fn, name)
 step = timeit(lambda: pipe.step(), "full step")
 print(f"sum of parts {tot*1e3:.1f} us; step {step*1e3:.1f} us -> {B/(step*1e-3):.0f} pairs/s")
 print("losses", pipe.losses[0].tolist())
-print("counts", pipe.counts.tolist())
+

@@ -30,11 +30,11 @@ def test_library_builds_and_exports_header_symbols():
 def test_argument_errors_are_reported_without_a_gpu():
     from delora_b200 import _lib
     L = _lib.lib()
-    rc = L.delora_normals_fwd(None, 1, 3, 4, 4, 7, 11, 0.5, 10, None, None)
+    rc = L.delora_normals_fwd(None, 1, 3, 4, 4, 7, 11, 0.5, 10, None, None, None, None)
     assert rc != 0
     assert b"null pointer" in L.delora_last_error()
     assert L.delora_scan_blocks(64 * 2048) == 128
-    assert L.delora_icp_blocks(1000) == 4
+    assert L.delora_icp_partial_rows(1000) == 32
 
 
 def test_sm100a_sass_present():

@@ -250,6 +250,39 @@ def test_pair_pipeline_end_to_end(name, golden, cuda_lib):
     assert rel_pl < 1e-4 and rel_nn < 1e-4 and gerr < 1e-3
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_dense_icp_matches_list_icp(name, golden, cuda_lib):
+    """The dense-grid kernel (training fast path) against the oracle and against the CSR kernel."""
+    from delora_b200 import ops
+    meta, cfg, _, _, t_pred, out = oracle_case(name, golden)
+    h, w = meta["H"], meta["W"]
+    hf, vf = fov(cfg)
+    images = torch.cat((out["image_1"], out["image_2"])).to(DEV)
+    _, pg, ng = ops.normals(images, grids=True)
+    T = t_pred[:3, :].reshape(1, 12).contiguous().to(DEV)
+    losses, grad_t = ops.icp_dense_fwd_bwd(pg[1:2].contiguous(), ng[1:2].contiguous(), T, pg[0:1].contiguous(),
+                                           ng[0:1].contiguous(), h, w, hf, vf)
+    # the oracle on the oracle's lists (normals differ at the 1e-7 level, so not bit-identical)
+    row = losses[0].cpu()
+    assert int(row[3]) == out["num_pairs"]
+    assert row[1].item() == pytest.approx(out["loss_po2pl"], rel=1e-5)
+    assert row[2].item() == pytest.approx(out["loss_pl2pl"], rel=1e-5)
+    g_ref = out["grad_T"].numpy()
+    assert np.abs(grad_t[0].cpu().numpy().reshape(3, 4) - g_ref).max() <= 1e-4 * np.abs(g_ref).max()
+    # CSR kernel on the lists of the same images: same pair count, same sums up to summation order
+    nrm_img = ops.normals(images)
+    pts4, nrm4, cs, counts = ops.lists_from_images(images, nrm_img)
+    l2, g2, _, _, _ = ops.icp_fwd_bwd(pts4[1:2].contiguous(), nrm4[1:2].contiguous(), counts[1:2].contiguous(), T,
+                                      pts4[0:1].contiguous(), nrm4[0:1].contiguous(), cs[0:1].contiguous(), h, w,
+                                      hf, vf)
+    assert float(l2[0, 3]) == float(row[3])
+    assert torch.allclose(l2[0, :3].cpu(), row[:3], rtol=2e-6, atol=0)
+    assert torch.allclose(g2.cpu(), grad_t.cpu(), rtol=1e-4, atol=1e-9)
+    # empty / invalid pixels of the dense grids
+    assert bool(((pg[:, :, 3].view(torch.int32) >= 0) == ((images[:, 0] != 0) & (images[:, 1] != 0)
+                                                          & (images[:, 2] != 0)).reshape(2, -1)).all())
+
+
 def test_generic_lists_shuffled_and_po2po(golden, cuda_lib):
     """Arbitrary (shuffled, with out-of-FOV points) lists through delora_grid_build; po2po on."""
     from delora_b200 import ops
