@@ -27,6 +27,8 @@ SIGNATURES = {
                                          c_void_p, c_void_p, c_void_p, c_void_p]),
     "delora_grid_build": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
                                   c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "delora_grids_from_projection": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                             c_void_p, c_void_p, c_void_p]),
     "delora_pack_lists": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "delora_icp_partial_rows": (c_int, [c_int]),
     "delora_icp_scratch_floats": (c_i64, [c_int, c_int]),

@@ -221,9 +221,50 @@ pack_lists_kernel(const float* __restrict__ pts, const float* __restrict__ nrm, 
     }
 }
 
+// Training-step layout: the projection kept one point per pixel (index_map) out of a scan whose
+// normals were precomputed per point (the reference sub-selects both lists with the projection's
+// point indices: src/deploy/deployer.py:258-261).  Gather them into the dense float4 grids.
+__global__ void __launch_bounds__(256)
+grids_from_projection_kernel(const float* __restrict__ points, const float* __restrict__ normal_lists,
+                             const int32_t* __restrict__ index_map, int C, int n_stride, int HW,
+                             float4* __restrict__ pts_grid, float4* __restrict__ nrm_grid) {
+    const int b = blockIdx.y, pix = blockIdx.x * 256 + threadIdx.x;
+    if (pix >= HW) return;
+    const int idx = index_map[(size_t)b * HW + pix];
+    const float inf = __int_as_float(0x7f800000);
+    float4 p = make_float4(inf, inf, inf, __int_as_float(-1)), q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx >= 0) {
+        const float* __restrict__ pb = points + (size_t)b * C * n_stride;
+        p = make_float4(__ldg(pb + idx), __ldg(pb + n_stride + idx), __ldg(pb + 2 * (size_t)n_stride + idx),
+                        __int_as_float(pix));
+        const float* __restrict__ nb = normal_lists + (size_t)b * 3 * n_stride;
+        const float nx = __ldg(nb + idx), ny = __ldg(nb + n_stride + idx), nz = __ldg(nb + 2 * (size_t)n_stride + idx);
+        const bool has = (nx != 0.0f) | (ny != 0.0f) | (nz != 0.0f);                     // icp_losses.py:48-52
+        q = make_float4(nx, ny, nz, has ? 1.0f : 0.0f);
+    }
+    pts_grid[(size_t)b * HW + pix] = p;
+    nrm_grid[(size_t)b * HW + pix] = q;
+}
+
 }  // namespace delora
 
 using namespace delora;
+
+extern "C" int delora_grids_from_projection(const float* points, const float* normal_lists,
+                                            const int32_t* index_map, int B, int C, int n_stride, int H, int W,
+                                            delora_f4* pts_grid, delora_f4* nrm_grid, void* stream) {
+    DELORA_CHECK_ARG(points && normal_lists && index_map && pts_grid && nrm_grid,
+                     "delora_grids_from_projection: null pointer");
+    DELORA_CHECK_ARG(B > 0 && B <= 65535 && C >= 3 && n_stride > 0 && H > 0 && W > 0,
+                     "delora_grids_from_projection: bad shape");
+    const int HW = H * W;
+    dim3 grid((HW + 255) / 256, B);
+    grids_from_projection_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, normal_lists, index_map, C, n_stride,
+                                                                         HW, (float4*)pts_grid, (float4*)nrm_grid);
+    DELORA_CHECK_LAUNCH("grids_from_projection_kernel");
+    return 0;
+}
+
 
 extern "C" int delora_scan_blocks(int n_cells) { return (n_cells + kScanTile - 1) / kScanTile; }
 

@@ -21,6 +21,10 @@ constexpr int kNormTH = 8;
 struct Sym3 { float a00, a01, a02, a11, a12, a22; };
 
 // Cyclic Jacobi for a symmetric 3x3; returns the eigenvector of the smallest eigenvalue.
+// The rotation parameters use the fast reciprocal / rsqrt units (MUFU): a Jacobi rotation only has
+// to be orthogonal (c^2 + s^2 = 1 to fp32 rounding, guaranteed by s = t*c, c = rsqrt(1 + t^2)) and
+// to shrink the off-diagonal entry; a 2-ulp error in the angle costs at most an extra sweep.  The
+// IEEE-exact divisions/square roots of the first version were ~45 % of the kernel's instructions.
 __device__ __forceinline__ void smallest_eigenvector(Sym3 m, float& nx, float& ny, float& nz) {
     float a[3][3] = {{m.a00, m.a01, m.a02}, {m.a01, m.a11, m.a12}, {m.a02, m.a12, m.a22}};
     float v[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
@@ -34,25 +38,30 @@ __device__ __forceinline__ void smallest_eigenvector(Sym3 m, float& nx, float& n
             const int p = (k == 2) ? 1 : 0;
             const int q = (k == 0) ? 1 : 2;
             const float apq = a[p][q];
-            if (apq == 0.0f) continue;
-            const float theta = (a[q][q] - a[p][p]) / (2.0f * apq);
-            const float t = copysignf(1.0f, theta) / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.0f)));
+            // theta = (aqq - app) / (2 apq);  t = sgn(theta) / (|theta| + sqrt(theta^2 + 1))
+            // written without a division by apq:  t = sgn * 2|apq| / (|d| + sqrt(d^2 + 4 apq^2)), d = aqq - app
+            const float d = a[q][q] - a[p][p];
+            const float two_apq = 2.0f * apq;
+            const float h2 = fmaf(d, d, two_apq * two_apq);
+            const float hyp = h2 * rsqrtf(fmaxf(h2, 1e-38f));
+            const float sgn = ((d >= 0.0f) == (apq >= 0.0f)) ? 1.0f : -1.0f;
+            const float t = (apq == 0.0f) ? 0.0f : sgn * __fdividef(fabsf(two_apq), fabsf(d) + hyp);
             const float c = rsqrtf(fmaf(t, t, 1.0f));
-            const float s = t * c;
-            const float tau = s / (1.0f + c);
+            const float sn = t * c;
+            const float tau = __fdividef(sn, 1.0f + c);
             a[p][p] -= t * apq;
             a[q][q] += t * apq;
             a[p][q] = 0.0f; a[q][p] = 0.0f;
             const int r = 3 - p - q;
             const float arp = a[r][p], arq = a[r][q];
-            a[r][p] = arp - s * (arq + tau * arp);
-            a[r][q] = arq + s * (arp - tau * arq);
+            a[r][p] = arp - sn * (arq + tau * arp);
+            a[r][q] = arq + sn * (arp - tau * arq);
             a[p][r] = a[r][p]; a[q][r] = a[r][q];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const float vip = v[i][p], viq = v[i][q];
-                v[i][p] = vip - s * (viq + tau * vip);
-                v[i][q] = viq + s * (vip - tau * viq);
+                v[i][p] = vip - sn * (viq + tau * vip);
+                v[i][q] = viq + sn * (vip - tau * viq);
             }
         }
     }
@@ -67,6 +76,139 @@ __device__ __forceinline__ void smallest_eigenvector(Sym3 m, float& nx, float& n
     nx *= inv; ny *= inv; nz *= inv;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path for the reference's 7 x 11 patch (config/config_datasets.yaml:33,60).
+// Tile = 32 columns x 16 rows per CTA of 128 threads; every thread owns FOUR vertically adjacent
+// pixels, so one shared-memory read of a neighbour feeds up to four patches (10 x 11 LDS.128 for
+// 4 x 77 taps: 2.8x less shared-memory traffic than one pixel per thread, which is what bounded
+// the first version: 128 B/clk/SM of LDS.128).  The halo is staged ALREADY CLAMPED (positions
+// outside the image replicate the edge pixel, exactly the reference's index clamp,
+// normal_computation.py:104-111), so the tap loops use constant offsets and no index math.
+// tile.w = |p|, or +inf for an all-zero pixel: "neighbour present" (range gate passed and
+// not (0,0,0), linalg.py:34-37) is then the single test !(|q.w - c.w| > eps).
+constexpr int kFastTW = 32, kFastTH = 16, kFastPix = 4, kFastA = 3, kFastB = 5;
+constexpr int kFastThreads = kFastTW * (kFastTH / kFastPix);            // 128
+constexpr int kFastTileW = kFastTW + 2 * kFastB;                        // 42
+constexpr int kFastTileH = kFastTH + 2 * kFastA;                        // 22
+
+__global__ void __launch_bounds__(kFastThreads)
+normals_7x11_kernel(const float* __restrict__ image, int C_img, int H, int W, float eps_range, int min_nb,
+                    float* __restrict__ normals, float4* __restrict__ pts_grid, float4* __restrict__ nrm_grid) {
+    __shared__ float4 tile[kFastTileH * kFastTileW];
+    const int bi = blockIdx.z;
+    const int u0 = blockIdx.x * kFastTW, v0 = blockIdx.y * kFastTH;
+    const size_t HW = (size_t)H * W;
+    const float* __restrict__ img = image + (size_t)bi * C_img * HW;
+    const float inf = __int_as_float(0x7f800000);
+
+    for (int i = threadIdx.x; i < kFastTileH * kFastTileW; i += kFastThreads) {
+        const int ly = i / kFastTileW, lx = i - ly * kFastTileW;
+        const int gv = min(max(v0 - kFastA + ly, 0), H - 1), gu = min(max(u0 - kFastB + lx, 0), W - 1);
+        const size_t o = (size_t)gv * W + gu;
+        const float x = __ldg(img + o), y = __ldg(img + HW + o), z = __ldg(img + 2 * HW + o);
+        const bool zero = (x == 0.0f) & (y == 0.0f) & (z == 0.0f);
+        tile[i] = make_float4(x, y, z, zero ? inf : range3(x, y, z));
+    }
+    __syncthreads();
+
+    const int lu = threadIdx.x % kFastTW, lr = threadIdx.x / kFastTW;       // lr: which group of 4 rows
+    const int u = u0 + lu, vb = v0 + lr * kFastPix;
+    if (u >= W || vb >= H) return;
+    // thread's window: tile rows [lr*4, lr*4 + 9], tile cols [lu, lu + 10]
+    const float4* __restrict__ base = tile + (lr * kFastPix) * kFastTileW + lu;
+
+    float4 c[kFastPix];
+    bool valid[kFastPix];
+#pragma unroll
+    for (int k = 0; k < kFastPix; ++k) {
+        c[k] = base[(k + kFastA) * kFastTileW + kFastB];
+        valid[k] = (vb + k < H) && c[k].x != 0.0f && c[k].y != 0.0f && c[k].z != 0.0f;     // :35
+    }
+    // pass 1: gated sums and counts
+    float sx[kFastPix], sy[kFastPix], sz[kFastPix];
+    int n[kFastPix];
+#pragma unroll
+    for (int k = 0; k < kFastPix; ++k) { sx[k] = sy[k] = sz[k] = 0.0f; n[k] = 0; }
+#pragma unroll 1
+    for (int du = 0; du < 2 * kFastB + 1; ++du) {
+#pragma unroll
+        for (int r = 0; r < kFastPix + 2 * kFastA; ++r) {
+            const float4 q = base[r * kFastTileW + du];
+#pragma unroll
+            for (int k = 0; k < kFastPix; ++k) {
+                if (r - k >= 0 && r - k <= 2 * kFastA) {                         // compile-time
+                    const bool present = !(fabsf(q.w - c[k].w) > eps_range);     // :56-59 + linalg.py:34-37
+                    sx[k] += present ? q.x : 0.0f; sy[k] += present ? q.y : 0.0f; sz[k] += present ? q.z : 0.0f;
+                    n[k] += present ? 1 : 0;
+                }
+            }
+        }
+    }
+    float mx[kFastPix], my[kFastPix], mz[kFastPix];
+    bool go[kFastPix];
+    bool any_go = false;
+    const float kt = (float)((2 * kFastA + 1) * (2 * kFastB + 1));
+#pragma unroll
+    for (int k = 0; k < kFastPix; ++k) {
+        go[k] = valid[k] && n[k] >= min_nb;                                       // :67-69
+        any_go |= go[k];
+        const float fn = (float)n[k];
+        mx[k] = __fdiv_rn(__fmul_rn(__fdiv_rn(sx[k], kt), kt), fn);               // linalg.py:41-42
+        my[k] = __fdiv_rn(__fmul_rn(__fdiv_rn(sy[k], kt), kt), fn);
+        mz[k] = __fdiv_rn(__fmul_rn(__fdiv_rn(sz[k], kt), kt), fn);
+    }
+    // pass 2: centred covariance
+    Sym3 s[kFastPix];
+#pragma unroll
+    for (int k = 0; k < kFastPix; ++k) s[k] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (any_go) {
+#pragma unroll 1
+        for (int du = 0; du < 2 * kFastB + 1; ++du) {
+#pragma unroll
+            for (int r = 0; r < kFastPix + 2 * kFastA; ++r) {
+                const float4 q = base[r * kFastTileW + du];
+#pragma unroll
+                for (int k = 0; k < kFastPix; ++k) {
+                    if (r - k >= 0 && r - k <= 2 * kFastA) {
+                        const bool present = !(fabsf(q.w - c[k].w) > eps_range);
+                        // absent neighbours contribute a zero difference (linalg.py:43-46)
+                        const float dx = present ? q.x - mx[k] : 0.0f, dy = present ? q.y - my[k] : 0.0f,
+                                    dz = present ? q.z - mz[k] : 0.0f;
+                        s[k].a00 = fmaf(dx, dx, s[k].a00); s[k].a01 = fmaf(dx, dy, s[k].a01);
+                        s[k].a02 = fmaf(dx, dz, s[k].a02); s[k].a11 = fmaf(dy, dy, s[k].a11);
+                        s[k].a12 = fmaf(dy, dz, s[k].a12); s[k].a22 = fmaf(dz, dz, s[k].a22);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kFastPix; ++k) {
+        const int v = vb + k;
+        if (v >= H) continue;
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        if (go[k]) {
+            const float f = __fdiv_rn(1.0f, (float)(n[k] - 1));                   // linalg.py:39, :56
+            Sym3 t = s[k];
+            t.a00 *= f; t.a01 *= f; t.a02 *= f; t.a11 *= f; t.a12 *= f; t.a22 *= f;
+            smallest_eigenvector(t, nx, ny, nz);                                  // torch.symeig, evec[:, :, 0]
+            if (nx * c[k].x + ny * c[k].y + nz * c[k].z > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }   // :79-81
+        }
+        const size_t pix = (size_t)v * W + u;
+        if (normals) {
+            float* __restrict__ out = normals + (size_t)bi * 3 * HW + pix;
+            out[0] = nx; out[HW] = ny; out[2 * HW] = nz;
+        }
+        if (pts_grid) {
+            pts_grid[(size_t)bi * HW + pix] = valid[k] ? make_float4(c[k].x, c[k].y, c[k].z, __int_as_float((int)pix))
+                                                       : make_float4(inf, inf, inf, __int_as_float(-1));
+            const bool has = (nx != 0.0f) | (ny != 0.0f) | (nz != 0.0f);          // icp_losses.py:48-52
+            nrm_grid[(size_t)bi * HW + pix] = make_float4(nx, ny, nz, has ? 1.0f : 0.0f);
+        }
+    }
+}
+
+// Generic patch sizes (and the first version of the kernel): one pixel per thread, runtime loops.
 // A, B: half sizes of the patch when known at compile time (loops unroll); -1 = runtime.
 template <int A_, int B_>
 __global__ void __launch_bounds__(kNormTW * kNormTH)
@@ -180,10 +322,10 @@ extern "C" int delora_normals_fwd(const float* image, int B, int C_img, int H, i
     const size_t smem = (size_t)(kNormTW + 2 * b) * (kNormTH + 2 * a) * sizeof(float4);
     dim3 grid((W + kNormTW - 1) / kNormTW, (H + kNormTH - 1) / kNormTH, B);
     cudaStream_t st = (cudaStream_t)stream;
-    if (a == 3 && b == 5) {
-        normals_kernel<3, 5><<<grid, kNormTW * kNormTH, smem, st>>>(image, C_img, H, W, a, b, epsilon_range,
-                                                                    min_neighbors, normals, (float4*)pts_grid,
-                                                                    (float4*)nrm_grid);
+    if (a == kFastA && b == kFastB) {
+        dim3 gridf((W + kFastTW - 1) / kFastTW, (H + kFastTH - 1) / kFastTH, B);
+        normals_7x11_kernel<<<gridf, kFastThreads, 0, st>>>(image, C_img, H, W, epsilon_range, min_neighbors, normals,
+                                                            (float4*)pts_grid, (float4*)nrm_grid);
     } else {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(normals_kernel<-1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -131,6 +131,21 @@ def grid_build(pts, nrm, n, h, w, hfov, vfov):
     return pts4, nrm4, cell_start
 
 
+def grids_from_projection(points, normal_lists, index_map):
+    """points [B,C,N], normal_lists [B,3,N], index_map [B,H,W] int32 -> pts_grid, nrm_grid [B,HW,4]."""
+    b, c, n = points.shape
+    _, h, w = index_map.shape
+    pg = torch.empty((b, h * w, 4), dtype=torch.float32, device=points.device)
+    ng = torch.empty((b, h * w, 4), dtype=torch.float32, device=points.device)
+    L = _lib.lib()
+    _lib.check(L.delora_grids_from_projection(_req(points, torch.float32, "points"),
+                                              _req(normal_lists, torch.float32, "normal_lists"),
+                                              _req(index_map, torch.int32, "index_map"), b, c, n, h, w,
+                                              pg.data_ptr(), ng.data_ptr(), _stream()),
+               "delora_grids_from_projection")
+    return pg, ng
+
+
 def pack_lists(pts, nrm, n):
     b, _, ns = pts.shape
     pts4 = torch.empty((b, ns, 4), dtype=torch.float32, device=pts.device)

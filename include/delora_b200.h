@@ -136,6 +136,14 @@ int delora_grid_build(const float* pts, const float* nrm, const int32_t* n, int 
                       delora_f4* pts4, delora_f4* nrm4, int32_t* cell_start, int32_t* cursor,
                       int32_t* scratch, void* stream);
 
+/* Dense grids for the training step: the scan's points and its per-point (precomputed) normals,
+ * gathered through the projection's pixel -> point index map (src/deploy/deployer.py:258-261).
+ * points [B,C,n_stride], normal_lists [B,3,n_stride], index_map [B,H,W] ->
+ * pts_grid/nrm_grid [B,H*W] float4 as delora_icp_dense_fwd_bwd expects them. */
+int delora_grids_from_projection(const float* points, const float* normal_lists, const int32_t* index_map,
+                                 int B, int C, int n_stride, int H, int W,
+                                 delora_f4* pts_grid, delora_f4* nrm_grid, void* stream);
+
 /* Pack channels-first lists to float4 (no sorting): pts4.w = bits(list index), nrm4.w = has_normal. */
 int delora_pack_lists(const float* pts, const float* nrm, const int32_t* n, int B, int n_stride,
                       delora_f4* pts4, delora_f4* nrm4, void* stream);

@@ -174,6 +174,23 @@ def main():
     print("quat: kornia-stub vs scipy max abs", float((t_ref[:, :3, :3] - r_scipy).abs().max()))
     np.savez_compressed(os.path.join(GOLDEN, "quaternion.npz"), quaternion=quat.numpy(), translation=trans.numpy(),
                         T=t_ref.numpy())
+    # ---- encoder + heads: reference model (small width) with fixed seed -> state_dict + outputs
+    mcfg = synthetic.fov_config(h=16, w=64, vfov_deg=(-15.0, 15.0))
+    mcfg.update({"pre_feature_extraction": False, "resnet_outputs": 64, "use_dropout": False, "layers": [2, 2, 2, 2],
+                 "factor_fewer_resnet_channels": 8, "activation_fct": "tanh", "use_single_mlp_at_output": False})
+    torch.manual_seed(1234)
+    ref_model = ref.model.OdometryModel(config=mcfg)
+    g2 = torch.Generator().manual_seed(99)
+    img_1 = torch.randn(2, 4, 16, 64, generator=g2)
+    img_2 = torch.randn(2, 4, 16, 64, generator=g2)
+    with torch.no_grad():
+        tr, rot = ref_model(image_1=img_1, image_2=img_2)
+        feats = ref_model.forward_features(image_1=img_1, image_2=img_2)
+    sd = {"sd::" + k: v.numpy() for k, v in ref_model.state_dict().items()}
+    np.savez_compressed(os.path.join(GOLDEN, "model_small.npz"), image_1=img_1.numpy(), image_2=img_2.numpy(),
+                        translation=tr.numpy(), rotation=rot.numpy(), x1=feats[0].numpy(), x4=feats[3].numpy(), **sd)
+    summary["model_small"] = {"params": int(sum(p.numel() for p in ref_model.parameters())),
+                              "keys": sorted(ref_model.state_dict().keys())}
     summary["_versions"] = {"torch": torch.__version__, "numpy": np.__version__,
                             "scipy": __import__("scipy").__version__, "numba": __import__("numba").__version__,
                             "reference": "leggedrobotics/delora @ 15a25ee (SURVEY.md header)"}

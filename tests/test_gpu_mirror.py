@@ -1,0 +1,195 @@
+"""-m gpu: the reference-API mirror (same class names, signatures, return shapes as the
+reference's modules) against the oracle / golden vectors."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, case_inputs, unsort_uv
+from oracle import delora_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cfg_for(meta, **extra):
+    from delora_b200 import synthetic
+    cfg = synthetic.fov_config(h=meta["H"], w=meta["W"], vfov_deg=tuple(meta["vfov_deg"]), device=DEV)
+    cfg.update(extra)
+    return cfg
+
+
+@pytest.mark.parametrize("name", ["small_16x180", "kitti_64x720"])
+def test_image_projection_layer_five_outputs(name, golden, cuda_lib):
+    from delora_b200.utility.projection import ImageProjectionLayer
+    meta = golden[name]
+    _, (scan_1, _, _, _) = case_inputs(meta)
+    cfg = cfg_for(meta)
+    layer = ImageProjectionLayer(config=cfg)
+    image, u, v, idx, i2p = layer(input=scan_1[None].to(DEV), dataset="kitti")
+    hf, vf = cfg["horizontal_field_of_view"], cfg["kitti"]["vertical_field_of_view"]
+    # integer stage against the oracle on the kernel's own (u, v); float (u, v) within 1e-3 px
+    rng = torch.norm(scan_1, dim=0)
+    order = torch.argsort(rng, stable=True)
+    u_orig = torch.empty_like(u[0].cpu()); u_orig[order] = u[0].cpu()
+    v_orig = torch.empty_like(v[0].cpu()); v_orig[order] = v[0].cpu()
+    io, uo, vo, idxo, i2po = orc.project_to_img(scan_1[None], meta["H"], meta["W"], hf, vf, uv_override=(u_orig, v_orig))
+    assert image.shape == io.shape and image.dtype == torch.float32 and str(image.device).startswith("cuda")
+    assert torch.equal(image.cpu(), io)
+    assert idx.dtype == torch.int64 and torch.equal(idx.cpu(), idxo), "survivors in ascending (range, index) order"
+    assert i2p.shape == i2po.shape and torch.equal(i2p.cpu(), i2po)
+    assert u.shape == (1, scan_1.shape[1]) and torch.equal(u.cpu(), uo) and torch.equal(v.cpu(), vo)
+    uc, vc, _, = orc.project_to_img(scan_1[None], meta["H"], meta["W"], hf, vf)[1:4]
+    assert (u.cpu() - uc).abs().max() < 1e-3 and (v.cpu() - vc).abs().max() < 1e-3
+
+
+def test_normals_computer_triple(golden, cuda_lib):
+    from delora_b200.preprocessing.normal_computation import NormalsComputer
+    meta = golden["kitti_64x720"]
+    z = np.load(os.path.join(GOLDEN, "kitti_64x720_sample.npz"))
+    _, (scan_1, _, _, _) = case_inputs(meta)
+    cfg = cfg_for(meta)
+    hf, vf = cfg["horizontal_field_of_view"], cfg["kitti"]["vertical_field_of_view"]
+    image = orc.project_to_img(scan_1[None], meta["H"], meta["W"], hf, vf)[0]
+    nc = NormalsComputer(config=cfg, dataset_name="kitti")
+    normals, has_normal, points = nc.compute_normal_vectors(image=image.to(DEV))
+    assert normals.shape == (meta["P"][0], 3) and has_normal.dtype == torch.bool and points.shape == normals.shape
+    stride = int(z["stride"][0])                                   # strided sample of the REFERENCE's output
+    assert np.array_equal(points[::stride].cpu().numpy(), z["points_1"])
+    assert np.array_equal(has_normal[::stride].cpu().numpy(), z["has_normal_1"])
+    err = np.linalg.norm(normals[::stride].cpu().numpy() - z["normals_1"], axis=1)
+    assert np.quantile(err, 0.99) < 2e-4 and (err > 1e-2).mean() < 5e-3
+
+
+@pytest.mark.parametrize("po2po,normal_loss", [(False, "squared"), (True, "linear")])
+def test_icp_losses_module_forward_backward(po2po, normal_loss, golden, cuda_lib):
+    from delora_b200.losses.icp_losses import ICPLosses
+    meta = golden["small_16x180"]
+    cfg, (scan_1, scan_2, _, t_pred) = case_inputs(meta)
+    out = orc.pair_forward_backward(scan_1, scan_2, t_pred, cfg, backward=False)
+    gcfg = cfg_for(meta, point_to_point_loss=po2po, normal_loss=normal_loss)
+    tm = t_pred.view(1, 4, 4)
+    src = orc.transform_point_cloud(tm, out["points_2"].t()[None]).contiguous()
+    src_n = orc.rotate_point_cloud(tm, out["normals_2"].t()[None]).contiguous()
+    tgt, tgt_n = out["points_1"].t()[None].contiguous(), out["normals_1"].t()[None].contiguous()
+    # oracle with autograd
+    so, sno = src.clone().requires_grad_(True), src_n.clone().requires_grad_(True)
+    lo, aux = orc.icp_losses(so, sno, tgt, tgt_n, point_to_point_loss=po2po, normal_loss=normal_loss, return_aux=True)
+    (2.0 * lo["loss_po2pl"] + 0.5 * lo["loss_pl2pl"] + lo["loss_po2po"]).sum().backward()
+    # mirror
+    sg, sng = src.clone().to(DEV).requires_grad_(True), src_n.clone().to(DEV).requires_grad_(True)
+    mod = ICPLosses(config=gcfg)
+    losses, plotting = mod(source_point_cloud_transformed=sg, source_normal_list_transformed=sng,
+                           target_point_cloud=tgt.to(DEV), target_normal_list=tgt_n.to(DEV),
+                           compute_pointwise_loss_bool=True)
+    assert set(losses) == {"loss_po2po", "loss_po2pl", "loss_po2pl_pointwise", "loss_pl2pl"}
+    (2.0 * losses["loss_po2pl"] + 0.5 * losses["loss_pl2pl"] + losses["loss_po2po"]).sum().backward()
+    for k in ("loss_po2pl", "loss_pl2pl", "loss_po2po"):
+        assert float(losses[k]) == pytest.approx(float(lo[k]), rel=1e-5, abs=1e-12), k
+    assert plotting["scan_2_transformed"].shape == (1, 3, aux["num_pairs"])
+    assert torch.equal(plotting["scan_2_transformed"].detach().cpu(), aux["source_points_where_normals"].detach())
+    assert losses["loss_po2pl_pointwise"].shape == (1, 3, aux["num_pairs"])
+    assert torch.allclose(sg.grad.cpu(), so.grad, rtol=1e-4, atol=1e-9)
+    assert torch.allclose(sng.grad.cpu(), sno.grad, rtol=1e-4, atol=1e-9)
+
+
+def test_geometry_handler_autograd(cuda_lib):
+    from delora_b200.models.model_parts import GeometryHandler
+    z = np.load(os.path.join(GOLDEN, "quaternion.npz"))
+    q = torch.from_numpy(z["quaternion"]).to(DEV).requires_grad_(True)
+    t = torch.from_numpy(z["translation"]).to(DEV).requires_grad_(True)
+    T = GeometryHandler.get_transformation_matrix_quaternion(translation=t, quaternion=q, device=DEV)
+    assert np.abs(T.detach().cpu().numpy() - z["T"]).max() < 5e-7
+    w = torch.randn(16, 4, 4, generator=torch.Generator().manual_seed(3))
+    (T * w.to(DEV)).sum().backward()
+    qo = torch.from_numpy(z["quaternion"]).requires_grad_(True)
+    to = torch.from_numpy(z["translation"]).requires_grad_(True)
+    (orc.transformation_matrix_quaternion(to, qo) * w).sum().backward()
+    assert torch.allclose(q.grad.cpu(), qo.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(t.grad.cpu(), to.grad, rtol=1e-6, atol=1e-7)
+
+
+def tiny_training_config(tmp_path, batch_size):
+    from delora_b200 import synthetic
+    cfg = synthetic.fov_config(h=16, w=180, vfov_deg=(-15.0, 15.0), device=DEV)
+    cfg.update({"pre_feature_extraction": False, "resnet_outputs": 64, "use_dropout": False, "layers": [1, 1, 1, 1],
+                "factor_fewer_resnet_channels": 8, "activation_fct": "tanh", "use_single_mlp_at_output": False,
+                "batch_size": batch_size, "learning_rate": 1e-4, "store_dataset_in_RAM": True,
+                "num_dataloader_workers": 0, "normalization_scaling": False, "inference_only": False,
+                "unsupervised_at_start": True, "mode": "training", "experiment": "test",
+                "training_run_name": "pytest_run", "run_name": "pytest_run", "checkpoint": None,
+                "checkpoint_dir": str(tmp_path)})
+    cfg["kitti"]["preprocessed_path"] = str(tmp_path / "pre")
+    cfg["kitti"]["data_identifiers"] = [0]
+    return cfg
+
+
+def write_preprocessed(tmp_path, n_scans=3):
+    """Preprocessed lists made by the oracle (CPU): [P,3] points + normals per scan."""
+    from delora_b200 import synthetic
+    seq = tmp_path / "pre" / "00"
+    (seq / "scans").mkdir(parents=True)
+    (seq / "normals").mkdir(parents=True)
+    cfg = synthetic.fov_config(h=16, w=180, vfov_deg=(-15.0, 15.0))
+    hf, vf = cfg["horizontal_field_of_view"], cfg["kitti"]["vertical_field_of_view"]
+    for k in range(n_scans):
+        s1, s2, _, _ = synthetic.make_pair(40 + k, w_raw=192, rings=16, vfov_deg=(-15.0, 15.0))
+        img = orc.project_to_img((s1 if k % 2 == 0 else s2)[None], 16, 180, hf, vf)[0]
+        normals, _, points = orc.compute_normal_vectors(img)
+        np.save(seq / "scans" / (format(k, "06d") + ".npy"), points.numpy())
+        np.save(seq / "normals" / (format(k, "06d") + ".npy"), normals.numpy())
+
+
+def test_deployer_step_matches_per_sample_reference_flow(tmp_path, cuda_lib):
+    """Batched step (B=2) vs the reference's per-sample flow restated with the oracle: projection of
+    the lists, sub-selection by the returned indices, ICP losses with the SAME predicted transforms,
+    and the cumulative `loss_pc` quirk of src/deploy/deployer.py:312."""
+    from delora_b200.deploy.trainer import Trainer
+    write_preprocessed(tmp_path, n_scans=3)
+    cfg = tiny_training_config(tmp_path, batch_size=2)
+    torch.manual_seed(0)
+    trainer = Trainer(config=cfg)
+    trainer.training_bool = False                                   # forward only
+    dicts = [trainer.dataset[0], trainer.dataset[1]]
+    for d in dicts:
+        for k in d:
+            if hasattr(d[k], "to"):
+                d[k] = d[k].to(DEV)
+    el = Trainer.new_epoch_losses()
+    el, T = trainer.step(preprocessed_dicts=dicts, epoch_losses=el)
+    T = T.detach().cpu()
+    hf, vf = cfg["horizontal_field_of_view"], cfg["kitti"]["vertical_field_of_view"]
+    run = {"po2pl": 0.0, "pl2pl": 0.0, "pc": 0.0}
+    for j, d in enumerate(dicts):
+        lists = {}
+        for key_s, key_n in (("scan_1", "normal_list_1"), ("scan_2", "normal_list_2")):
+            s, n = d[key_s].cpu(), d[key_n].cpu()
+            idx = orc.project_to_img(s, 16, 180, hf, vf)[3]
+            lists[key_s], lists[key_n] = s[:, :, idx], n[:, :, idx]           # deployer.py:258-261
+        src = orc.transform_point_cloud(T[j:j + 1], lists["scan_2"])
+        src_n = orc.rotate_point_cloud(T[j:j + 1], lists["normal_list_2"])
+        lo = orc.icp_losses(src, src_n, lists["scan_1"].contiguous(), lists["normal_list_1"].contiguous())
+        run["po2pl"] += float(lo["loss_po2pl"])
+        run["pl2pl"] += float(lo["loss_pl2pl"])
+        run["pc"] += run["po2pl"] + run["pl2pl"]                            # :309-312 (running sums!)
+    assert float(el["loss_po2pl_epoch"]) == pytest.approx(run["po2pl"] / 2, rel=2e-5)
+    assert float(el["loss_pl2pl_epoch"]) == pytest.approx(run["pl2pl"] / 2, rel=2e-5)
+    assert float(el["loss_point_cloud_epoch"]) == pytest.approx(run["pc"] / 2, rel=2e-5)
+
+
+def test_trainer_runs_and_checkpoints(tmp_path, cuda_lib):
+    from delora_b200.deploy.trainer import Trainer
+    write_preprocessed(tmp_path, n_scans=3)
+    cfg = tiny_training_config(tmp_path, batch_size=1)
+    torch.manual_seed(0)
+    trainer = Trainer(config=cfg)
+    before = [p.detach().clone() for p in trainer.model.parameters()]
+    hist = trainer.train(max_epochs=2)
+    assert len(hist) == 2 and all(np.isfinite(hist))
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, trainer.model.parameters())), "weights moved"
+    ckpt = torch.load(tmp_path / "pytest_run_latest_checkpoint.pth", weights_only=False)
+    assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "loss", "parameters"}
+    assert "resnet.conv1.weight" in ckpt["model_state_dict"]
+    assert "fully_connected_rotation.1.weight" in ckpt["model_state_dict"]

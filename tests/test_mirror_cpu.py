@@ -1,0 +1,135 @@
+"""-m "not gpu": host-side logic of the reference-API mirror (model parameter names / forward vs
+the reference's own model, dataset indexing, CLI config merge, gradient all-reduce over gloo)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, ROOT
+
+
+def small_model_config():
+    from delora_b200 import synthetic
+    cfg = synthetic.fov_config(h=16, w=64, vfov_deg=(-15.0, 15.0))
+    cfg.update({"pre_feature_extraction": False, "resnet_outputs": 64, "use_dropout": False, "layers": [2, 2, 2, 2],
+                "factor_fewer_resnet_channels": 8, "activation_fct": "tanh", "use_single_mlp_at_output": False})
+    return cfg
+
+
+def test_model_state_dict_interchanges_with_reference(golden):
+    """Load the REFERENCE model's state_dict (golden) into the mirror and reproduce its outputs."""
+    from delora_b200.models.model import OdometryModel
+    z = np.load(os.path.join(GOLDEN, "model_small.npz"))
+    model = OdometryModel(config=small_model_config())
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    assert sorted(model.state_dict().keys()) == golden["model_small"]["keys"]
+    model.load_state_dict(sd, strict=True)
+    assert sum(p.numel() for p in model.parameters()) == golden["model_small"]["params"]
+    with torch.no_grad():
+        tr, rot = model(image_1=torch.from_numpy(z["image_1"]), image_2=torch.from_numpy(z["image_2"]))
+        feats = model.forward_features(image_1=torch.from_numpy(z["image_1"]), image_2=torch.from_numpy(z["image_2"]))
+    assert np.allclose(feats[0].numpy(), z["x1"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(feats[3].numpy(), z["x4"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(tr.numpy(), z["translation"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(rot.numpy(), z["rotation"], rtol=1e-5, atol=1e-6)
+
+
+def test_full_size_model_parameter_count():
+    """11,675,112 encoder + 100,504 rotation + 100,403 translation parameters."""
+    from delora_b200.models.model import OdometryModel
+    cfg = small_model_config()
+    cfg.update({"resnet_outputs": 1000, "factor_fewer_resnet_channels": 1})
+    model = OdometryModel(config=cfg)
+    assert sum(p.numel() for p in model.resnet.parameters()) == 11675112
+    assert sum(p.numel() for p in model.fully_connected_rotation.parameters()) == 100504
+    assert sum(p.numel() for p in model.fully_connected_translation.parameters()) == 100403
+
+
+def write_tiny_dataset(root, n_scans=4, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    seq = os.path.join(root, "00")
+    os.makedirs(os.path.join(seq, "scans"))
+    os.makedirs(os.path.join(seq, "normals"))
+    for k in range(n_scans):
+        p = 50 + 7 * k
+        np.save(os.path.join(seq, "scans", format(k, "06d") + ".npy"), torch.randn(p, 3, generator=g).numpy())
+        np.save(os.path.join(seq, "normals", format(k, "06d") + ".npy"), torch.randn(p, 3, generator=g).numpy())
+
+
+def test_dataset_layout_and_keys(tmp_path):
+    from delora_b200.data.dataset import PreprocessedPointCloudDataset
+    write_tiny_dataset(str(tmp_path))
+    cfg = {"datasets": ["kitti"], "store_dataset_in_RAM": False,
+           "kitti": {"preprocessed_path": str(tmp_path), "data_identifiers": [0]}}
+    ds = PreprocessedPointCloudDataset(config=cfg)
+    assert len(ds) == 3                                           # consecutive pairs (t, t+1)
+    item = ds[1]
+    assert set(item) == {"index", "index_dataset", "index_sequence", "index_scan", "dataset", "normal_list_1",
+                         "normal_list_2", "scan_1", "scan_2"}
+    assert item["scan_1"].shape == (1, 3, 57) and item["scan_2"].shape == (1, 3, 64)
+    assert item["dataset"] == "kitti" and item["index_scan"] == 1
+    cfg["store_dataset_in_RAM"] = True
+    ds2 = PreprocessedPointCloudDataset(config=cfg)
+    assert torch.equal(ds2[1]["scan_2"], item["scan_2"])
+    cfg["kitti"]["data_identifiers"] = [7]
+    with pytest.raises(Exception, match="does not exist"):
+        PreprocessedPointCloudDataset(config=cfg)
+
+
+def test_cli_config_merge_matches_reference_yaml(tmp_path):
+    """bin/run_training.py::build_config on a copy of the reference-format YAML files."""
+    sys.path.insert(0, os.path.join(ROOT, "bin"))
+    import run_training
+    cdir = tmp_path / "config"
+    cdir.mkdir()
+    (cdir / "config_datasets.yaml").write_text(
+        "horizontal_field_of_view: [ -179.9, 179.9 ]\nepsilon_range: 0.5\n"
+        "kitti:\n  training_identifiers: [ 0 ]\n  vertical_field_of_view: [ -24.5, 2.0 ]\n"
+        "  vertical_cells: 64\n  horizontal_cells: 720\n")
+    (cdir / "deployment_options.yaml").write_text('datasets: ["kitti"]\ndevice: "cpu"\nexperiment: "e"\n')
+    (cdir / "hyperparameters.yaml").write_text("batch_size: 1\nlearning_rate: 0.00001\n")
+    cfg = run_training.build_config("run", "exp", "", config_dir=str(cdir))
+    assert cfg["kitti"]["vertical_field_of_view"][0] == pytest.approx(-24.5 * np.pi / 180.0)
+    assert cfg["horizontal_field_of_view"][1] == pytest.approx(179.9 * np.pi / 180.0)
+    assert cfg["kitti"]["data_identifiers"] == [0] and cfg["mode"] == "training" and cfg["experiment"] == "exp"
+    assert cfg["device"] == torch.device("cpu") and cfg["run_name"] == "run" and cfg["checkpoint"] is None
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from delora_b200.parallel_grad import FlatGradAllReduce, shard_pairs
+    torch.manual_seed(100 + rank)                                  # different init per rank -> broadcast must fix it
+    model = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 3))
+    sync = FlatGradAllReduce(model)
+    x = torch.arange(8 * 5, dtype=torch.float32).view(8, 5) / 10.0
+    shard = shard_pairs(8, rank, world)
+    model(x[shard]).pow(2).sum().backward()
+    sync.all_reduce()
+    flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    w0 = torch.cat([p.data.reshape(-1) for p in model.parameters()])
+    torch.save({"grad": flat, "w": w0, "shard": shard}, os.path.join(out, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world_size_2_gloo(tmp_path):
+    """Two gloo ranks, each on its own shard of the pairs: after the flat all-reduce both hold the
+    average of the two shard gradients == the gradient of the half-summed full batch."""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
+    assert r0["shard"] == [0, 1, 2, 3] and r1["shard"] == [4, 5, 6, 7]
+    assert torch.equal(r0["w"], r1["w"]), "parameters are broadcast from rank 0"
+    assert torch.allclose(r0["grad"], r1["grad"], rtol=0, atol=0)
+    # single-process check
+    torch.manual_seed(100)
+    model = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 3))
+    x = torch.arange(8 * 5, dtype=torch.float32).view(8, 5) / 10.0
+    (model(x).pow(2).sum() / 2).backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert torch.allclose(r0["grad"], ref, rtol=1e-5, atol=1e-6)
