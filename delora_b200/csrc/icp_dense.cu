@@ -40,9 +40,11 @@ struct NN2 {
     int j1;
 };
 
-__device__ __forceinline__ void nn2_eval(const float4 t, int j, float sx, float sy, float sz, NN2& s) {
+__device__ __forceinline__ void nn2_eval(const float4 t, int j, float sx, float sy, float sz, NN2& s,
+                                         bool ok = true) {
     const float dx = sx - t.x, dy = sy - t.y, dz = sz - t.z;
-    const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float d2f = ok ? d2 : __int_as_float(0x7f800000);      // out-of-grid rows / idle lanes never win
     const bool lt = d2f < s.m1;
     s.m2 = lt ? s.m1 : fminf(s.m2, d2f);
     s.j1 = lt ? j : s.j1;
@@ -125,26 +127,26 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
         // fully unrolled: 15 independent loads in flight
         int e_dn = 1, e_up = 1, e_lf = 2, e_rt = 2;
         if (H >= 3 && W >= 5) {
+            int col[5];
+#pragma unroll
+            for (int dc = -2; dc <= 2; ++dc) col[dc + 2] = wrap_col(cc + dc, W);
 #pragma unroll
             for (int dr = -1; dr <= 1; ++dr) {
                 const int row = rc + dr;
                 const bool rok = active && row >= 0 && row < H;
+                const int rbase = min(max(row, 0), H - 1) * W;          // always a valid address
 #pragma unroll
-                for (int dc = -2; dc <= 2; ++dc) {
-                    const int j = row * W + wrap_col(cc + dc, W);
-                    nn2_eval(rok ? __ldg(tg + j) : inf4(), j, sx, sy, sz, nn);
-                }
+                for (int dc = 0; dc < 5; ++dc) nn2_eval(__ldg(tg + rbase + col[dc]), rbase + col[dc], sx, sy, sz, nn, rok);
             }
         } else {
             e_dn = e_up = e_lf = e_rt = 0;
-            if (active) nn2_eval(__ldg(tg + rc * W + cc), rc * W + cc, sx, sy, sz, nn);
+            nn2_eval(__ldg(tg + rc * W + cc), rc * W + cc, sx, sy, sz, nn, active);
         }
+        float b_dn = (rc - e_dn > 0) ? border_bound(f_dn + (float)e_dn, g.dv_rad, r) : kInf;
+        float b_up = (rc + e_up < H - 1) ? border_bound(f_up + (float)e_up, g.dv_rad, r) : kInf;
+        float b_lf = (e_lf + e_rt + 1 >= W) ? kInf : border_bound(f_lf + (float)e_lf, g.du_rad, rxy);
+        float b_rt = (e_lf + e_rt + 1 >= W) ? kInf : border_bound(f_rt + (float)e_rt, g.du_rad, rxy);
         while (true) {
-            const float b_dn = (rc - e_dn > 0) ? border_bound(f_dn + (float)e_dn, g.dv_rad, r) : kInf;
-            const float b_up = (rc + e_up < H - 1) ? border_bound(f_up + (float)e_up, g.dv_rad, r) : kInf;
-            const bool full_w = (e_lf + e_rt + 1 >= W);
-            const float b_lf = full_w ? kInf : border_bound(f_lf + (float)e_lf, g.du_rad, rxy);
-            const float b_rt = full_w ? kInf : border_bound(f_rt + (float)e_rt, g.du_rad, rxy);
             const float bmin = fminf(fminf(b_dn, b_up), fminf(b_lf, b_rt));
             const bool done = !active || bmin >= kInf ||
                               (nn.j1 >= 0 && sqrtf(nn.m1) * 1.00001f <= bmin * 0.9995f);
@@ -155,25 +157,35 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
             if (side < 2) {
                 const int row = (side == 0) ? rc - (++e_dn) : rc + (++e_up);
                 const bool rok = active && row >= 0 && row < H;
+                const int rbase = min(max(row, 0), H - 1) * W;
                 const int n = e_lf + e_rt + 1;
+                int col = wrap_col(cc - e_lf, W);
 #pragma unroll 4
                 for (int k = 0; k < n; ++k) {
-                    const int j = row * W + wrap_col(cc - e_lf + k, W);
-                    nn2_eval(rok ? __ldg(tg + j) : inf4(), j, sx, sy, sz, nn);
+                    nn2_eval(__ldg(tg + rbase + col), rbase + col, sx, sy, sz, nn, rok);
+                    ++col;
+                    col = (col == W) ? 0 : col;
                 }
+                if (side == 0) b_dn = (rc - e_dn > 0) ? border_bound(f_dn + (float)e_dn, g.dv_rad, r) : kInf;
+                else           b_up = (rc + e_up < H - 1) ? border_bound(f_up + (float)e_up, g.dv_rad, r) : kInf;
             } else {
                 const int step = min(2, W - (e_lf + e_rt + 1));
                 const int c0 = wrap_col((side == 2) ? cc - e_lf - 1 : cc + e_rt + 1, W);
                 const int c1 = wrap_col((side == 2) ? cc - e_lf - 2 : cc + e_rt + 2, W);
                 const int n = e_dn + e_up + 1;
+                const bool two = (step == 2);
 #pragma unroll 2
                 for (int k = 0; k < n; ++k) {
                     const int row = rc - e_dn + k;
                     const bool rok = active && row >= 0 && row < H;
-                    nn2_eval(rok ? __ldg(tg + row * W + c0) : inf4(), row * W + c0, sx, sy, sz, nn);
-                    if (step == 2) nn2_eval(rok ? __ldg(tg + row * W + c1) : inf4(), row * W + c1, sx, sy, sz, nn);
+                    const int rbase = min(max(row, 0), H - 1) * W;
+                    nn2_eval(__ldg(tg + rbase + c0), rbase + c0, sx, sy, sz, nn, rok);
+                    nn2_eval(__ldg(tg + rbase + c1), rbase + c1, sx, sy, sz, nn, rok && two);
                 }
                 if (side == 2) e_lf += step; else e_rt += step;
+                const bool full_w = (e_lf + e_rt + 1 >= W);
+                b_lf = full_w ? kInf : border_bound(f_lf + (float)e_lf, g.du_rad, rxy);
+                b_rt = full_w ? kInf : border_bound(f_rt + (float)e_rt, g.du_rad, rxy);
             }
         }
         best_j = nn.j1;

@@ -136,7 +136,10 @@ def test_projection_matches_torch_cuda_op_sequence(golden, cuda_lib):
     same_uv = float(((ut == u_g) & (vt == v_g)).float().mean())
     same_img = float((image_t[0].cpu() == image_g).float().mean())
     print(f"[torch-cuda op sequence] identical (u,v): {same_uv:.6f}, identical image entries: {same_img:.6f}")
-    assert same_uv > 0.999 and same_img > 0.999
+    # torch-CUDA's own float pipeline differs from torch-CPU's by an ulp in most (u, v) (measured: only
+    # ~14 % of the float coordinates are bit-identical), yet the IMAGES agree except at rounding
+    # boundaries -- the same statement as for CPU-vs-kernel.  Informational for (u,v); asserted for pixels.
+    assert same_img > 0.9995
 
 
 def test_sort_by_range(golden, cuda_lib):
