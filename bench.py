@@ -130,6 +130,13 @@ def max_over_ranks(x, world, device):
     return float(t[0])
 
 
+def cpu_threads():
+    """Threads for the CPU arm.  Measured on the B200 box's host (2 x Xeon 8562Y+, 128 hardware threads;
+    profiles/r01_cpu_threads.log): 8 -> 4.00 s/pair, 16 -> 3.53, 32 -> 4.22, 64 -> 5.40, 128 -> 23.4.
+    The reference's many small torch ops oversubscribe badly, so its best setting (16) is used."""
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
 def cpu_reference_step(raw_pair, cfg):
     """One pair through the oracle port of the reference's CPU path (fwd + bwd to the transform)."""
     from oracle import delora_oracle as orc
@@ -145,7 +152,7 @@ def run_reference(args):
     if rank != 0:
         return
     from delora_b200 import synthetic
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     cfg = synthetic.fov_config(h=H, w=W)
     pairs = [synthetic.make_pair(i, w_raw=W_RAW) for i in range(2)]
@@ -164,7 +171,7 @@ def run_reference(args):
                                "1 pair per step on the host CPU", "pairs_per_step": 1, "H": H, "W": W},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps x 1 pair (oracle port of the reference CPU path, "
-                                   f"torch {torch.__version__} CPU, {cores} threads)"},
+                                   f"torch {torch.__version__} CPU, {cores} of {os.cpu_count()} threads = best of a sweep)"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -290,7 +297,7 @@ def run_ours(args):
                         "CUDA-event duration inside the timed region; see `kernels` for every operator"}
 
     # ---------------- CPU baseline: oracle port on a bounded sample --------------------------
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     cpu_n = args.cpu_pairs
     out, cpu_dt, cpu_value = {"loss_po2pl": None, "loss_pl2pl": None}, 0.0, None
@@ -320,7 +327,8 @@ def run_ours(args):
         "roofline": roofline, "kernels": kernels,
         "cpu_baseline": {"value": cpu_value, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"{cpu_n} pairs at 64x2048 through oracle.pair_forward_backward "
-                                   f"(torch {torch.__version__} CPU + scipy cKDTree), {cpu_dt:.1f} s"},
+                                   f"(torch {torch.__version__} CPU + scipy cKDTree), {cores} of {os.cpu_count()} host threads "
+                                   f"(best of a sweep), {cpu_dt:.1f} s"},
         "clocks": clocks, "wall_s_timed_region": t_wall,
         "check": {"loss_po2pl": losses0[1], "loss_pl2pl": losses0[2], "pairs": losses0[3],
                   "cpu_loss_po2pl": out["loss_po2pl"], "cpu_loss_pl2pl": out["loss_pl2pl"]},

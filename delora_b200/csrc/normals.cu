@@ -32,7 +32,9 @@ __device__ __forceinline__ void smallest_eigenvector(Sym3 m, float& nx, float& n
     for (int sweep = 0; sweep < 8; ++sweep) {
         const float off = fabsf(a[0][1]) + fabsf(a[0][2]) + fabsf(a[1][2]);
         const float diag = fabsf(a[0][0]) + fabsf(a[1][1]) + fabsf(a[2][2]);
-        if (off <= 1e-12f * diag || off == 0.0f) break;
+        // fp32 convergence: off-diagonal mass below one ulp of the diagonal mass (Jacobi converges
+        // quadratically: typically 3-4 sweeps; a stricter test never fires in fp32 and just burns sweeps)
+        if (off <= 3e-8f * diag) break;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int p = (k == 2) ? 1 : 0;
@@ -124,63 +126,95 @@ normals_7x11_kernel(const float* __restrict__ image, int C_img, int H, int W, fl
         c[k] = base[(k + kFastA) * kFastTileW + kFastB];
         valid[k] = (vb + k < H) && c[k].x != 0.0f && c[k].y != 0.0f && c[k].z != 0.0f;     // :35
     }
-    // pass 1: gated sums and counts
-    float sx[kFastPix], sy[kFastPix], sz[kFastPix];
-    int n[kFastPix];
+    // The four pixels are processed as two PAIRS in packed fp32x2 arithmetic (Blackwell FFMA2 /
+    // FADD2 / FMUL2: one instruction per two fp32 lanes, IEEE round-to-nearest per lane, so the
+    // numbers are those of the scalar code).  A neighbour outside one pixel's 7 rows gets weight 0.
+    constexpr int kPairs = kFastPix / 2;
+    // pass 1: gated sums and counts  (weights w in {0,1}: fma(w, q, s) == s + q or s exactly)
+    float2 sx[kPairs], sy[kPairs], sz[kPairs], cnt[kPairs];
 #pragma unroll
-    for (int k = 0; k < kFastPix; ++k) { sx[k] = sy[k] = sz[k] = 0.0f; n[k] = 0; }
+    for (int p = 0; p < kPairs; ++p) sx[p] = sy[p] = sz[p] = cnt[p] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int du = 0; du < 2 * kFastB + 1; ++du) {
 #pragma unroll
         for (int r = 0; r < kFastPix + 2 * kFastA; ++r) {
             const float4 q = base[r * kFastTileW + du];
 #pragma unroll
-            for (int k = 0; k < kFastPix; ++k) {
-                if (r - k >= 0 && r - k <= 2 * kFastA) {                         // compile-time
-                    const bool present = !(fabsf(q.w - c[k].w) > eps_range);     // :56-59 + linalg.py:34-37
-                    sx[k] += present ? q.x : 0.0f; sy[k] += present ? q.y : 0.0f; sz[k] += present ? q.z : 0.0f;
-                    n[k] += present ? 1 : 0;
+            for (int p = 0; p < kPairs; ++p) {
+                const bool in0 = (r - 2 * p >= 0) && (r - 2 * p <= 2 * kFastA);             // compile-time
+                const bool in1 = (r - 2 * p - 1 >= 0) && (r - 2 * p - 1 <= 2 * kFastA);
+                if (in0 || in1) {
+                    const bool g0 = in0 && !(fabsf(q.w - c[2 * p].w) > eps_range);          // :56-59 + linalg.py:34-37
+                    const bool g1 = in1 && !(fabsf(q.w - c[2 * p + 1].w) > eps_range);
+                    const float2 w = make_float2(g0 ? 1.0f : 0.0f, g1 ? 1.0f : 0.0f);
+                    sx[p] = __ffma2_rn(w, make_float2(q.x, q.x), sx[p]);
+                    sy[p] = __ffma2_rn(w, make_float2(q.y, q.y), sy[p]);
+                    sz[p] = __ffma2_rn(w, make_float2(q.z, q.z), sz[p]);
+                    cnt[p] = __fadd2_rn(cnt[p], w);
                 }
             }
         }
     }
+    int n[kFastPix];
     float mx[kFastPix], my[kFastPix], mz[kFastPix];
     bool go[kFastPix];
     bool any_go = false;
     const float kt = (float)((2 * kFastA + 1) * (2 * kFastB + 1));
 #pragma unroll
     for (int k = 0; k < kFastPix; ++k) {
+        const float fn = (k & 1) ? cnt[k / 2].y : cnt[k / 2].x;
+        const float ssx = (k & 1) ? sx[k / 2].y : sx[k / 2].x, ssy = (k & 1) ? sy[k / 2].y : sy[k / 2].x,
+                    ssz = (k & 1) ? sz[k / 2].y : sz[k / 2].x;
+        n[k] = (int)fn;
         go[k] = valid[k] && n[k] >= min_nb;                                       // :67-69
         any_go |= go[k];
-        const float fn = (float)n[k];
-        mx[k] = __fdiv_rn(__fmul_rn(__fdiv_rn(sx[k], kt), kt), fn);               // linalg.py:41-42
-        my[k] = __fdiv_rn(__fmul_rn(__fdiv_rn(sy[k], kt), kt), fn);
-        mz[k] = __fdiv_rn(__fmul_rn(__fdiv_rn(sz[k], kt), kt), fn);
+        mx[k] = __fdiv_rn(__fmul_rn(__fdiv_rn(ssx, kt), kt), fn);                 // linalg.py:41-42
+        my[k] = __fdiv_rn(__fmul_rn(__fdiv_rn(ssy, kt), kt), fn);
+        mz[k] = __fdiv_rn(__fmul_rn(__fdiv_rn(ssz, kt), kt), fn);
     }
-    // pass 2: centred covariance
-    Sym3 s[kFastPix];
+    // pass 2: centred covariance, e = w * (q - mean), cov += e (q - mean)^T
+    float2 a00[kPairs], a01[kPairs], a02[kPairs], a11[kPairs], a12[kPairs], a22[kPairs];
 #pragma unroll
-    for (int k = 0; k < kFastPix; ++k) s[k] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p < kPairs; ++p) a00[p] = a01[p] = a02[p] = a11[p] = a12[p] = a22[p] = make_float2(0.f, 0.f);
     if (any_go) {
+        float2 nmx[kPairs], nmy[kPairs], nmz[kPairs];
+#pragma unroll
+        for (int p = 0; p < kPairs; ++p) {
+            nmx[p] = make_float2(-mx[2 * p], -mx[2 * p + 1]);
+            nmy[p] = make_float2(-my[2 * p], -my[2 * p + 1]);
+            nmz[p] = make_float2(-mz[2 * p], -mz[2 * p + 1]);
+        }
 #pragma unroll 1
         for (int du = 0; du < 2 * kFastB + 1; ++du) {
 #pragma unroll
             for (int r = 0; r < kFastPix + 2 * kFastA; ++r) {
                 const float4 q = base[r * kFastTileW + du];
 #pragma unroll
-                for (int k = 0; k < kFastPix; ++k) {
-                    if (r - k >= 0 && r - k <= 2 * kFastA) {
-                        const bool present = !(fabsf(q.w - c[k].w) > eps_range);
-                        // absent neighbours contribute a zero difference (linalg.py:43-46)
-                        const float dx = present ? q.x - mx[k] : 0.0f, dy = present ? q.y - my[k] : 0.0f,
-                                    dz = present ? q.z - mz[k] : 0.0f;
-                        s[k].a00 = fmaf(dx, dx, s[k].a00); s[k].a01 = fmaf(dx, dy, s[k].a01);
-                        s[k].a02 = fmaf(dx, dz, s[k].a02); s[k].a11 = fmaf(dy, dy, s[k].a11);
-                        s[k].a12 = fmaf(dy, dz, s[k].a12); s[k].a22 = fmaf(dz, dz, s[k].a22);
+                for (int p = 0; p < kPairs; ++p) {
+                    const bool in0 = (r - 2 * p >= 0) && (r - 2 * p <= 2 * kFastA);
+                    const bool in1 = (r - 2 * p - 1 >= 0) && (r - 2 * p - 1 <= 2 * kFastA);
+                    if (in0 || in1) {
+                        const bool g0 = in0 && !(fabsf(q.w - c[2 * p].w) > eps_range);
+                        const bool g1 = in1 && !(fabsf(q.w - c[2 * p + 1].w) > eps_range);
+                        const float2 w = make_float2(g0 ? 1.0f : 0.0f, g1 ? 1.0f : 0.0f);
+                        const float2 dx = __fadd2_rn(make_float2(q.x, q.x), nmx[p]);     // linalg.py:43
+                        const float2 dy = __fadd2_rn(make_float2(q.y, q.y), nmy[p]);
+                        const float2 dz = __fadd2_rn(make_float2(q.z, q.z), nmz[p]);
+                        const float2 ex = __fmul2_rn(dx, w), ey = __fmul2_rn(dy, w), ez = __fmul2_rn(dz, w);   // :44-45
+                        a00[p] = __ffma2_rn(ex, dx, a00[p]); a01[p] = __ffma2_rn(ex, dy, a01[p]);      // :46, :54
+                        a02[p] = __ffma2_rn(ex, dz, a02[p]); a11[p] = __ffma2_rn(ey, dy, a11[p]);
+                        a12[p] = __ffma2_rn(ey, dz, a12[p]); a22[p] = __ffma2_rn(ez, dz, a22[p]);
                     }
                 }
             }
         }
+    }
+    Sym3 s[kFastPix];
+#pragma unroll
+    for (int k = 0; k < kFastPix; ++k) {
+        const int p = k / 2;
+        s[k] = (k & 1) ? Sym3{a00[p].y, a01[p].y, a02[p].y, a11[p].y, a12[p].y, a22[p].y}
+                       : Sym3{a00[p].x, a01[p].x, a02[p].x, a11[p].x, a12[p].x, a22[p].x};
     }
 #pragma unroll
     for (int k = 0; k < kFastPix; ++k) {
