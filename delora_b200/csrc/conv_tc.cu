@@ -1,0 +1,439 @@
+// Encoder convolutions on the 5th-generation tensor cores (sm_100a): implicit GEMM, forward.
+//
+// Replaces the cuDNN calls behind `torch.nn.Conv2d` in the reference's encoder
+// (src/models/resnet_modified.py:40 stem, :126-134 conv3x3/conv1x1, used at :95-120, :159-177):
+// 3x3 (and 1x1 downsample) convolutions, no bias, circular padding along the image width
+// (CircularPad / F.pad(mode='circular'), :97,:100,:162,:167), zero padding along the height
+// (padding=(1,0)), strides (1,1), (1,2), (2,2), followed by tanh / relu and, for the second conv
+// of a BasicBlock, the residual add before the activation (:174-175).
+//
+// Layout: activations are NHWC bf16 with the padding MATERIALISED: [B, H+2, W+2, C]; rows 0 and
+// H+1 are zero, column 0 is a copy of column W and column W+1 a copy of column 1 (the epilogue of
+// the producing kernel writes both copies), so every filter tap of an output tile is a plain
+// shifted box of the same tensor -> one TMA load per tap and K-chunk, no im2col buffer:
+//     GEMM  M = 128 output pixels (TW along w x TH along h),  N = BN output channels,
+//           K = taps x Cin, walked as (tap, 64-channel chunk).
+// A (pixels x 64 ch) and B (BN filters x 64 ch) tiles are K-major, 128-byte swizzled, written by
+// TMA (cp.async.bulk.tensor) into a 4-stage shared-memory ring; one elected thread issues
+// tcgen05.mma (M=128, N=BN, K=16, bf16 -> fp32) with the accumulator in tensor memory;
+// tcgen05.commit releases the stage; four epilogue warps read their TMEM lane quarter with
+// tcgen05.ld, add the residual, apply the activation, convert to bf16 and store NHWC (plus the
+// circular halo columns).  Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM allocator,
+// 2..5 = epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cudaTypedefs.h>
+#include "common.cuh"
+
+namespace delora {
+
+constexpr int kConvThreads = 192;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;           // bf16 elements = 128 bytes = one swizzle row
+constexpr int kStages = 4;
+constexpr int kUmmaK = 16;
+
+struct ConvParams {
+    int B, Hout, Wout, Cin, Cout;
+    int taps, ksize;                  // 9/3 or 1/1
+    int stride_h, stride_w;
+    int pad_off;                      // 0 for 3x3 (tap offset starts at padded coord 0), 1 for 1x1
+    int TW, TH;                       // output tile: TW x TH = 128 pixels
+    int tiles_w, tiles_h;             // tiles per image row / column
+    int BN;
+    int act;                          // 0 none, 1 relu, 2 tanh
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4 | LBO (unused for swizzled K-major) = 1 | SBO = 1024 B (8 rows x 128 B) | version 1 |
+// layout_type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.0f);
+    if (act == 2) {           // MUFU.TANH: 2^-11 relative error, far below the bf16 output rounding
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v));
+        return t;
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y, ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B swizzle atoms
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = kBlockM * kBlockK * 2;            // 16 KB
+    const int b_bytes = p.BN * kBlockK * 2;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * a_bytes;
+    uint64_t* full_bar = (uint64_t*)(smem_b + kStages * b_bytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates: blockIdx.x -> (b, tile_h, tile_w), blockIdx.y -> n tile
+    int t = blockIdx.x;
+    const int tw_i = t % p.tiles_w; t /= p.tiles_w;
+    const int th_i = t % p.tiles_h; t /= p.tiles_h;
+    const int b = t;
+    const int wo0 = tw_i * p.TW, ho0 = th_i * p.TH;
+    const int n0 = blockIdx.y * p.BN;
+    const int kchunks = p.Cin / kBlockK;
+    const int n_iter = p.taps * kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // allocate BN TMEM columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                     "r"((uint32_t)p.BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+            for (int it = 0; it < n_iter; ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(empty_bar + s, ph ^ 1);
+                const int tap = it / kchunks, kc = it - tap * kchunks;
+                const int r = tap / p.ksize, q = tap - r * p.ksize;
+                mbar_expect_tx(full_bar + s, (uint32_t)(a_bytes + b_bytes));
+                tma_load_4d(smem_a + s * a_bytes, &map_x, full_bar + s, kc * kBlockK, wo0 * p.stride_w + q + p.pad_off,
+                            ho0 * p.stride_h + r + p.pad_off, b);
+                tma_load_2d(smem_b + s * b_bytes, &map_w, full_bar + s, tap * p.Cin + kc * kBlockK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                               ((uint32_t)(kBlockM >> 4) << 24);
+        for (int it = 0; it < n_iter; ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(full_bar + s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint64_t da = make_smem_desc(smem_u32(smem_a + s * a_bytes));
+                const uint64_t db = make_smem_desc(smem_u32(smem_b + s * b_bytes));
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+                    tcgen05_mma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                     (it > 0 || k > 0) ? 1u : 0u);
+                }
+                tcgen05_commit(empty_bar + s);                       // frees the smem stage when the MMAs retire
+                if (it == n_iter - 1) tcgen05_commit(tmem_full_bar); // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue warps 2..5 =====================
+        const int quarter = warp & 3;                                // TMEM lanes 32*quarter .. +31
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int m = quarter * 32 + lane;                           // row of the tile = output pixel
+        const int wo = wo0 + (m % p.TW), ho = ho0 + (m / p.TW);
+        const bool in_range = (wo < p.Wout) && (ho < p.Hout);
+        const int Wp = p.Wout + 2, Hp = p.Hout + 2;
+        const size_t pix = ((size_t)b * Hp + (ho + 1)) * Wp + (wo + 1);
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
+            if (in_range) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                if (residual) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * p.Cout + n0 + c0);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const uint4 rv = __ldg(rp + j4);
+                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __bfloat1622float2(h[e]);
+                            v[j4 * 8 + e * 2] += f.x; v[j4 * 8 + e * 2 + 1] += f.y;
+                        }
+                    }
+                }
+                uint4 out[4];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    __nv_bfloat162 h[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        h[e] = __floats2bfloat162_rn(apply_act(v[j4 * 8 + e * 2], p.act), apply_act(v[j4 * 8 + e * 2 + 1], p.act));
+                    out[j4] = *reinterpret_cast<uint4*>(h);
+                }
+                uint4* yp = reinterpret_cast<uint4*>(y + pix * p.Cout + n0 + c0);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) yp[j4] = out[j4];
+                // circular halo columns of the padded output (read by the next layer's taps)
+                if (wo == 0) {
+                    uint4* hp = reinterpret_cast<uint4*>(y + (pix + p.Wout) * p.Cout + n0 + c0);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) hp[j4] = out[j4];
+                }
+                if (wo == p.Wout - 1) {
+                    uint4* hp = reinterpret_cast<uint4*>(y + (pix - p.Wout) * p.Cout + n0 + c0);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) hp[j4] = out[j4];
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.BN));
+    }
+}
+
+// ---------------------------------------------------------------- layout helpers (bandwidth kernels)
+// two [B,4,H,W] fp32 range images -> [B, H+2, W+2, Cpad] bf16, channels 0..7 = cat(image_1, image_2)
+// (src/models/model.py:98), the rest zero; circular halo columns, zero halo rows.
+__global__ void __launch_bounds__(256)
+images_to_nhwc_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int B, int H, int W, int Cpad,
+                      __nv_bfloat16* __restrict__ x) {
+    const int Wp = W + 2, Hp = H + 2;
+    const size_t total = (size_t)B * Hp * Wp;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int wp = (int)(i % Wp), hp = (int)((i / Wp) % Hp), b = (int)(i / ((size_t)Wp * Hp));
+    __nv_bfloat16* o = x + i * Cpad;
+    const bool zero_row = (hp == 0) || (hp == Hp - 1);
+    int w = wp - 1;
+    if (w < 0) w = W - 1;
+    if (w >= W) w = 0;
+    const int h = hp - 1;
+    for (int c = 0; c < Cpad; ++c) {
+        float v = 0.0f;
+        if (!zero_row && c < 8) {
+            const float* src = (c < 4) ? img1 : img2;
+            v = __ldg(src + (((size_t)b * 4 + (c & 3)) * H + h) * W + w);
+        }
+        o[c] = __float2bfloat16_rn(v);
+    }
+}
+
+// MaxPool2d(3, stride (1,2), padding (1,0)) after circular W padding (src/models/resnet_modified.py:46,:100-101),
+// NHWC padded in / out; the height padding of the pool is -inf (PyTorch), i.e. rows outside are skipped.
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, __nv_bfloat16* __restrict__ y) {
+    const int Wout = W / 2;
+    const size_t total = (size_t)B * H * Wout * (C / 2);
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int c2 = (int)(i % (C / 2));
+    size_t r = i / (C / 2);
+    const int wo = (int)(r % Wout); r /= Wout;
+    const int ho = (int)(r % H);
+    const int b = (int)(r / H);
+    const int Wp = W + 2, Hp = H + 2, Wpo = Wout + 2;
+    float m0 = -INFINITY, m1 = -INFINITY;
+    for (int dr = -1; dr <= 1; ++dr) {
+        const int h = ho + dr;
+        if (h < 0 || h >= H) continue;
+        for (int dq = 0; dq < 3; ++dq) {
+            const int wp = 2 * wo + dq;                  // padded column index (circular halo materialised)
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(
+                x + (((size_t)b * Hp + h + 1) * Wp + wp) * C + 2 * c2);
+            const float2 f = __bfloat1622float2(v);
+            m0 = fmaxf(m0, f.x); m1 = fmaxf(m1, f.y);
+        }
+    }
+    const __nv_bfloat162 o = __floats2bfloat162_rn(m0, m1);
+    const size_t pix = ((size_t)b * Hp + ho + 1) * Wpo + wo + 1;
+    *reinterpret_cast<__nv_bfloat162*>(y + pix * C + 2 * c2) = o;
+    if (wo == 0) *reinterpret_cast<__nv_bfloat162*>(y + (pix + Wout) * C + 2 * c2) = o;
+    if (wo == Wout - 1) *reinterpret_cast<__nv_bfloat162*>(y + (pix - Wout) * C + 2 * c2) = o;
+}
+
+// padded NHWC bf16 -> NCHW fp32 (interior only): the reference's feature-map layout, for checks / heads
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, float* __restrict__ y) {
+    const size_t total = (size_t)B * C * H * W;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int w = (int)(i % W), h = (int)((i / W) % H), c = (int)((i / ((size_t)W * H)) % C);
+    const int b = (int)(i / ((size_t)W * H * C));
+    y[i] = __bfloat162float(x[(((size_t)b * (H + 2) + h + 1) * (W + 2) + w + 1) * C + c]);
+}
+
+// ---------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }
+    return fn;
+}
+
+}  // namespace delora
+
+using namespace delora;
+
+extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void* residual, void* y, int B, int Hin,
+                                        int Win, int Cin, int Cout, int ksize, int stride_h, int stride_w, int act,
+                                        void* stream) {
+    DELORA_CHECK_ARG(x && w && y, "delora_conv2d_fprop_bf16: null pointer");
+    DELORA_CHECK_ARG(ksize == 3 || ksize == 1, "delora_conv2d_fprop_bf16: kernel size %d unsupported", ksize);
+    DELORA_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0, "delora_conv2d_fprop_bf16: Cin=%d, Cout=%d must be multiples of 64",
+                     Cin, Cout);
+    DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin % stride_h == 0 &&
+                         Win % stride_w == 0, "delora_conv2d_fprop_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
+    ConvParams p;
+    p.B = B; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
+    p.stride_h = stride_h; p.stride_w = stride_w; p.pad_off = (ksize == 1) ? 1 : 0; p.act = act;
+    p.Hout = Hin / stride_h; p.Wout = Win / stride_w;
+    p.TW = p.Wout >= 128 ? 128 : p.Wout;
+    DELORA_CHECK_ARG(128 % p.TW == 0 && p.Wout % p.TW == 0, "delora_conv2d_fprop_bf16: Wout=%d must divide or be divided by 128",
+                     p.Wout);
+    p.TH = 128 / p.TW;
+    p.tiles_w = p.Wout / p.TW;
+    p.tiles_h = (p.Hout + p.TH - 1) / p.TH;
+    p.BN = (Cout % 128 == 0) ? 128 : 64;
+    PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode();
+    DELORA_CHECK_ARG(encode != nullptr, "delora_conv2d_fprop_bf16: cuTensorMapEncodeTiled not available");
+    const int Hp = Hin + 2, Wp = Win + 2;
+    CUtensorMap map_x, map_w;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Wp * Cin * 2, (cuuint64_t)Hp * Wp * Cin * 2};
+        // with a traversal stride the box spans TW*stride_w (TH*stride_h) elements and loads every stride-th one
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.TW * stride_w), (cuuint32_t)(p.TH * stride_h), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
+        CUresult r = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DELORA_CHECK_ARG(r == CUDA_SUCCESS, "delora_conv2d_fprop_bf16: tensor map (activations) failed: %d", (int)r);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)p.taps * Cin, (cuuint64_t)Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)p.taps * Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)p.BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DELORA_CHECK_ARG(r == CUDA_SUCCESS, "delora_conv2d_fprop_bf16: tensor map (weights) failed: %d", (int)r);
+    }
+    const size_t smem = (size_t)kStages * (kBlockM * kBlockK * 2 + p.BN * kBlockK * 2) + (2 * kStages + 1) * 8 + 16 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    DELORA_CHECK_ARG(e == cudaSuccess, "delora_conv2d_fprop_bf16: smem opt-in failed: %s", cudaGetErrorString(e));
+    dim3 grid(B * p.tiles_h * p.tiles_w, Cout / p.BN);
+    conv_fprop_tc_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(
+        map_x, map_w, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, p);
+    DELORA_CHECK_LAUNCH("conv_fprop_tc_kernel");
+    return 0;
+}
+
+extern "C" int delora_images_to_nhwc_bf16(const float* image_1, const float* image_2, int B, int H, int W, int Cpad,
+                                          void* x, void* stream) {
+    DELORA_CHECK_ARG(image_1 && image_2 && x && Cpad >= 8 && Cpad % 8 == 0, "delora_images_to_nhwc_bf16: bad argument");
+    const size_t total = (size_t)B * (H + 2) * (W + 2);
+    images_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        image_1, image_2, B, H, W, Cpad, (__nv_bfloat16*)x);
+    DELORA_CHECK_LAUNCH("images_to_nhwc_kernel");
+    return 0;
+}
+
+extern "C" int delora_maxpool_w_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* stream) {
+    DELORA_CHECK_ARG(x && y && W % 2 == 0 && C % 2 == 0, "delora_maxpool_w_nhwc_bf16: bad argument");
+    const size_t total = (size_t)B * H * (W / 2) * (C / 2);
+    maxpool_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, B, H, W, C, (__nv_bfloat16*)y);
+    DELORA_CHECK_LAUNCH("maxpool_nhwc_kernel");
+    return 0;
+}
+
+extern "C" int delora_nhwc_to_nchw_f32(const void* x, int B, int H, int W, int C, float* y, void* stream) {
+    DELORA_CHECK_ARG(x && y, "delora_nhwc_to_nchw_f32: null pointer");
+    const size_t total = (size_t)B * C * H * W;
+    nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, B, H, W, C, y);
+    DELORA_CHECK_LAUNCH("nhwc_to_nchw_kernel");
+    return 0;
+}

@@ -247,3 +247,56 @@ def quat_to_T_bwd(quaternion, grad_t):
                                       _req(grad_t, torch.float32, "grad_T"), b, gq.data_ptr(), gt.data_ptr(),
                                       _stream()), "delora_quat_to_T_bwd")
     return gq, gt
+
+
+# ---------------------------------------------------------------------------------------------
+# encoder (tcgen05 implicit-GEMM convolutions, bf16 NHWC with materialised padding)
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+
+
+def padded_nhwc_zeros(b, h, w, c, device):
+    """[B, H+2, W+2, C] bf16, all zero (the conv epilogue never touches the zero halo rows)."""
+    return torch.zeros((b, h + 2, w + 2, c), dtype=torch.bfloat16, device=device)
+
+
+def conv2d_fprop(x, weight, hin, win, ksize, stride, act=ACT_NONE, residual=None, out=None):
+    """x [B,Hin+2,Win+2,Cin] bf16 padded NHWC, weight [Cout,k*k,Cin] bf16 -> y [B,Hout+2,Wout+2,Cout]."""
+    b, _, _, cin = x.shape
+    cout = weight.shape[0]
+    hout, wout = hin // stride[0], win // stride[1]
+    if out is None:
+        out = padded_nhwc_zeros(b, hout, wout, cout, x.device)
+    L = _lib.lib()
+    _lib.check(L.delora_conv2d_fprop_bf16(_req(x, torch.bfloat16, "x"), _req(weight, torch.bfloat16, "weight"),
+                                          _req(residual, torch.bfloat16, "residual") if residual is not None else None,
+                                          out.data_ptr(), b, hin, win, cin, cout, ksize, stride[0], stride[1], int(act),
+                                          _stream()), "delora_conv2d_fprop_bf16")
+    return out
+
+
+def images_to_nhwc(image_1, image_2, cpad=64):
+    b, _, h, w = image_1.shape
+    x = torch.empty((b, h + 2, w + 2, cpad), dtype=torch.bfloat16, device=image_1.device)
+    L = _lib.lib()
+    _lib.check(L.delora_images_to_nhwc_bf16(_req(image_1, torch.float32, "image_1"),
+                                            _req(image_2, torch.float32, "image_2"), b, h, w, cpad, x.data_ptr(),
+                                            _stream()), "delora_images_to_nhwc_bf16")
+    return x
+
+
+def maxpool_w(x, h, w):
+    b, _, _, c = x.shape
+    y = padded_nhwc_zeros(b, h, w // 2, c, x.device)
+    L = _lib.lib()
+    _lib.check(L.delora_maxpool_w_nhwc_bf16(_req(x, torch.bfloat16, "x"), b, h, w, c, y.data_ptr(), _stream()),
+               "delora_maxpool_w_nhwc_bf16")
+    return y
+
+
+def nhwc_to_nchw(x, h, w):
+    b, _, _, c = x.shape
+    y = torch.empty((b, c, h, w), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    _lib.check(L.delora_nhwc_to_nchw_f32(_req(x, torch.bfloat16, "x"), b, h, w, c, y.data_ptr(), _stream()),
+               "delora_nhwc_to_nchw_f32")
+    return y

@@ -208,6 +208,31 @@ int delora_icp_point_grads(const delora_f4* point_dir, const delora_f4* normal_d
                            int src_stride, int B, const float* losses, const float* upstream,
                            float* grad_pts, float* grad_nrm, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Encoder convolution, forward, on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM, bf16 out).
+ * Replaces the cuDNN call behind torch.nn.Conv2d in the reference's encoder
+ *   (src/models/resnet_modified.py:40 stem, :126-134 conv3x3 / conv1x1; used at :95-120, :159-177)
+ *   including the circular width padding (:97, :162, :167), the zero height padding, the
+ *   activation and the residual add of BasicBlock.forward (:174-175).
+ * x        [B, Hin+2, Win+2, Cin]  bf16 NHWC with materialised padding (rows 0/Hin+1 zero, column 0 =
+ *          column Win, column Win+1 = column 1)
+ * w        [Cout, ksize*ksize, Cin] bf16 (tap-major K: torch weight.permute(0,2,3,1))
+ * residual [B, Hout+2, Wout+2, Cout] bf16 or NULL, added before the activation
+ * y        [B, Hout+2, Wout+2, Cout] bf16 out (interior + circular halo columns are written; the
+ *          zero halo rows must have been zeroed once by the caller)
+ * ksize 3 (pad 1 in H, wrap in W) or 1 (no padding); stride_h/w in {1,2}; act: 0 none, 1 relu, 2 tanh.
+ * Cin, Cout multiples of 64 (the 8-channel stem input is channel-padded by delora_images_to_nhwc_bf16). */
+int delora_conv2d_fprop_bf16(const void* x, const void* w, const void* residual, void* y, int B, int Hin, int Win,
+                             int Cin, int Cout, int ksize, int stride_h, int stride_w, int act, void* stream);
+
+/* cat(image_1, image_2) ([B,4,H,W] fp32 each, src/models/model.py:98) -> [B,H+2,W+2,Cpad] bf16 padded NHWC */
+int delora_images_to_nhwc_bf16(const float* image_1, const float* image_2, int B, int H, int W, int Cpad,
+                               void* x, void* stream);
+/* MaxPool2d(3, stride (1,2), padding (1,0)) on the W-wrapped input (src/models/resnet_modified.py:46,:100-101) */
+int delora_maxpool_w_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* stream);
+/* padded NHWC bf16 -> NCHW fp32 (interior), the reference's feature-map layout */
+int delora_nhwc_to_nchw_f32(const void* x, int B, int H, int W, int C, float* y, void* stream);
+
 /* quaternion (x, y, z, w) + translation -> 4x4, and its backward.
  * Replaces models.model_parts.GeometryHandler.get_transformation_matrix_quaternion
  *   (src/models/model_parts.py:37-44 -> kornia 0.3.0 quaternion_to_rotation_matrix).
