@@ -30,7 +30,7 @@ namespace delora {
 constexpr int kConvThreads = 192;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;           // bf16 elements = 128 bytes = one swizzle row
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;         // smem ring depth is chosen per launch so that two CTAs fit on one SM
 constexpr int kUmmaK = 16;
 
 struct ConvParams {
@@ -42,6 +42,7 @@ struct ConvParams {
     int tiles_w, tiles_h;             // tiles per image row / column
     int BN;
     int act;                          // 0 none, 1 relu, 2 tanh
+    int stages;                       // smem ring depth (<= kMaxStages)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -122,7 +123,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // ---------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)
 conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                      const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y, ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -130,11 +131,12 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int a_bytes = kBlockM * kBlockK * 2;            // 16 KB
     const int b_bytes = p.BN * kBlockK * 2;
+    const int kStages = p.stages;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * a_bytes;
     uint64_t* full_bar = (uint64_t*)(smem_b + kStages * b_bytes);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -273,25 +275,31 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 __global__ void __launch_bounds__(256)
 images_to_nhwc_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int B, int H, int W, int Cpad,
                       __nv_bfloat16* __restrict__ x) {
-    const int Wp = W + 2, Hp = H + 2;
-    const size_t total = (size_t)B * Hp * Wp;
+    // one thread per (padded pixel, group of 8 channels): 16-byte stores, a pixel's Cpad channels are
+    // written by Cpad/8 adjacent threads (coalesced); only group 0 carries data (8 real channels)
+    const int Wp = W + 2, Hp = H + 2, groups = Cpad / 8;
+    const size_t total = (size_t)B * Hp * Wp * groups;
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= total) return;
-    const int wp = (int)(i % Wp), hp = (int)((i / Wp) % Hp), b = (int)(i / ((size_t)Wp * Hp));
-    __nv_bfloat16* o = x + i * Cpad;
-    const bool zero_row = (hp == 0) || (hp == Hp - 1);
-    int w = wp - 1;
-    if (w < 0) w = W - 1;
-    if (w >= W) w = 0;
-    const int h = hp - 1;
-    for (int c = 0; c < Cpad; ++c) {
-        float v = 0.0f;
-        if (!zero_row && c < 8) {
-            const float* src = (c < 4) ? img1 : img2;
-            v = __ldg(src + (((size_t)b * 4 + (c & 3)) * H + h) * W + w);
+    const int grp = (int)(i % groups);
+    const size_t pixel = i / groups;
+    const int wp = (int)(pixel % Wp), hp = (int)((pixel / Wp) % Hp), b = (int)(pixel / ((size_t)Wp * Hp));
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (grp == 0 && hp != 0 && hp != Hp - 1) {
+        int w = wp - 1;
+        if (w < 0) w = W - 1;
+        if (w >= W) w = 0;
+        const int h = hp - 1;
+        __nv_bfloat162 v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float* src = (c < 2) ? img1 : img2;
+            const size_t base = (((size_t)b * 4 + (2 * c & 3)) * H + h) * W + w;
+            v[c] = __floats2bfloat162_rn(__ldg(src + base), __ldg(src + base + (size_t)H * W));
         }
-        o[c] = __float2bfloat16_rn(v);
+        out = *reinterpret_cast<uint4*>(v);
     }
+    *reinterpret_cast<uint4*>(x + pixel * Cpad + grp * 8) = out;
 }
 
 // MaxPool2d(3, stride (1,2), padding (1,0)) after circular W padding (src/models/resnet_modified.py:46,:100-101),
@@ -351,6 +359,57 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     return fn;
 }
 
+struct TensorMaps {
+    CUtensorMap x, w;
+};
+
+// Tensor maps depend only on (pointers, shapes); encoding them costs a few microseconds of host time
+// per call, which matters when 20 convolutions are launched back to back.  Small per-thread cache.
+static const TensorMaps* get_maps(const void* x, const void* w, int B, int Hin, int Win, int Cin, int Cout,
+                                  const ConvParams& p) {
+    struct Key { const void* x; const void* w; int B, Hin, Win, Cin, Cout, ks, sh, sw; };
+    struct Entry { Key k; TensorMaps m; };
+    static thread_local Entry cache[64];
+    static thread_local int used = 0, next = 0;
+    const Key key = {x, w, B, Hin, Win, Cin, Cout, p.ksize, p.stride_h, p.stride_w};
+    for (int i = 0; i < used; ++i) {
+        const Key& c = cache[i].k;
+        if (c.x == key.x && c.w == key.w && c.B == key.B && c.Hin == key.Hin && c.Win == key.Win && c.Cin == key.Cin &&
+            c.Cout == key.Cout && c.ks == key.ks && c.sh == key.sh && c.sw == key.sw)
+            return &cache[i].m;
+    }
+    PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode();
+    if (!encode) return nullptr;
+    Entry& e = cache[next];
+    const int Hp = Hin + 2, Wp = Win + 2;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Wp * Cin * 2, (cuuint64_t)Hp * Wp * Cin * 2};
+        // with a traversal stride the box spans TW*stride_w (TH*stride_h) elements and loads every stride-th one
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.TW * p.stride_w), (cuuint32_t)(p.TH * p.stride_h), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)p.stride_w, (cuuint32_t)p.stride_h, 1};
+        if (encode(&e.m.x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return nullptr;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)p.taps * Cin, (cuuint64_t)Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)p.taps * Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)p.BN};
+        cuuint32_t estr[2] = {1, 1};
+        if (encode(&e.m.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return nullptr;
+    }
+    e.k = key;
+    const TensorMaps* out = &e.m;
+    next = (next + 1) % 64;
+    if (used < 64) ++used;
+    return out;
+}
+
 }  // namespace delora
 
 using namespace delora;
@@ -375,37 +434,21 @@ extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void
     p.tiles_w = p.Wout / p.TW;
     p.tiles_h = (p.Hout + p.TH - 1) / p.TH;
     p.BN = (Cout % 128 == 0) ? 128 : 64;
-    PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode();
-    DELORA_CHECK_ARG(encode != nullptr, "delora_conv2d_fprop_bf16: cuTensorMapEncodeTiled not available");
-    const int Hp = Hin + 2, Wp = Win + 2;
-    CUtensorMap map_x, map_w;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Wp * Cin * 2, (cuuint64_t)Hp * Wp * Cin * 2};
-        // with a traversal stride the box spans TW*stride_w (TH*stride_h) elements and loads every stride-th one
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.TW * stride_w), (cuuint32_t)(p.TH * stride_h), 1};
-        cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
-        CUresult r = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        DELORA_CHECK_ARG(r == CUDA_SUCCESS, "delora_conv2d_fprop_bf16: tensor map (activations) failed: %d", (int)r);
+    // two CTAs per SM: one CTA's epilogue overlaps the other's main loop (ring = 3 stages of 32 KB for
+    // BN = 128, 4 stages of 24 KB for BN = 64; TMEM: 2 x BN <= 512 columns)
+    p.stages = (p.BN == 128) ? 3 : 4;
+    const TensorMaps* maps = get_maps(x, w, B, Hin, Win, Cin, Cout, p);
+    DELORA_CHECK_ARG(maps != nullptr, "delora_conv2d_fprop_bf16: cuTensorMapEncodeTiled failed or is unavailable");
+    const size_t smem = (size_t)p.stages * (kBlockM * kBlockK * 2 + p.BN * kBlockK * 2) + (2 * kMaxStages + 1) * 8 + 16 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        DELORA_CHECK_ARG(e == cudaSuccess, "delora_conv2d_fprop_bf16: smem opt-in failed: %s", cudaGetErrorString(e));
+        attr_set = true;
     }
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)p.taps * Cin, (cuuint64_t)Cout};
-        cuuint64_t strides[1] = {(cuuint64_t)p.taps * Cin * 2};
-        cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)p.BN};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        DELORA_CHECK_ARG(r == CUDA_SUCCESS, "delora_conv2d_fprop_bf16: tensor map (weights) failed: %d", (int)r);
-    }
-    const size_t smem = (size_t)kStages * (kBlockM * kBlockK * 2 + p.BN * kBlockK * 2) + (2 * kStages + 1) * 8 + 16 + 1024;
-    cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    DELORA_CHECK_ARG(e == cudaSuccess, "delora_conv2d_fprop_bf16: smem opt-in failed: %s", cudaGetErrorString(e));
     dim3 grid(B * p.tiles_h * p.tiles_w, Cout / p.BN);
     conv_fprop_tc_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(
-        map_x, map_w, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, p);
+        maps->x, maps->w, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, p);
     DELORA_CHECK_LAUNCH("conv_fprop_tc_kernel");
     return 0;
 }
@@ -413,7 +456,7 @@ extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void
 extern "C" int delora_images_to_nhwc_bf16(const float* image_1, const float* image_2, int B, int H, int W, int Cpad,
                                           void* x, void* stream) {
     DELORA_CHECK_ARG(image_1 && image_2 && x && Cpad >= 8 && Cpad % 8 == 0, "delora_images_to_nhwc_bf16: bad argument");
-    const size_t total = (size_t)B * (H + 2) * (W + 2);
+    const size_t total = (size_t)B * (H + 2) * (W + 2) * (Cpad / 8);
     images_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         image_1, image_2, B, H, W, Cpad, (__nv_bfloat16*)x);
     DELORA_CHECK_LAUNCH("images_to_nhwc_kernel");

@@ -55,7 +55,23 @@ class OdometryModel(torch.nn.Module):
             x = torch.cat((image_1, image_2), dim=1)
         return self.resnet(x)
 
+    def _tensor_core_path(self):
+        """Inference (eval mode, no grad) can run the encoder on the tcgen05 convolution kernels
+        (`models/tc_encoder.py`); training keeps the differentiable torch path until the dgrad / wgrad
+        kernels exist.  Opt-in with config["use_tensor_core_encoder"] = True."""
+        if not self.config.get("use_tensor_core_encoder", False) or self.training or torch.is_grad_enabled():
+            return None
+        if self.pre_feature_extraction or self.config["factor_fewer_resnet_channels"] != 1:
+            return None
+        if getattr(self, "_tc_encoder", None) is None:
+            from . import tc_encoder
+            self._tc_encoder = tc_encoder.TensorCoreEncoder(self)
+        return self._tc_encoder
+
     def forward(self, image_1, image_2):
+        tc = self._tensor_core_path()
+        if tc is not None:
+            return tc.forward(image_1.contiguous(), image_2.contiguous())
         x = self.forward_features(image_1=image_1, image_2=image_2)[-1]
         if self.config["use_single_mlp_at_output"]:
             x = self.fully_connected_rot_trans(x)

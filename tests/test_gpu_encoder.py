@@ -1,0 +1,91 @@
+"""-m gpu: tcgen05 implicit-GEMM convolution and the tensor-core encoder against torch
+(fp32 math on bf16-rounded operands for the single layer; the fp32 cuDNN model for the stack)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def to_padded_nhwc(x):
+    xp = F.pad(F.pad(x, (1, 1, 0, 0), mode="circular"), (0, 0, 1, 1))
+    return xp.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+CASES = [  # B, Cin, Cout, H, W, k, stride, act, residual
+    (1, 64, 64, 8, 128, 3, (1, 1), 0, False),
+    (2, 64, 64, 16, 256, 3, (1, 1), 2, True),
+    (2, 64, 128, 16, 256, 3, (1, 2), 2, False),
+    (2, 64, 128, 16, 256, 1, (1, 2), 0, False),
+    (2, 128, 128, 16, 128, 3, (1, 1), 1, True),
+    (2, 256, 512, 16, 128, 3, (2, 2), 2, False),
+    (2, 256, 512, 16, 128, 1, (2, 2), 0, False),
+    (1, 512, 512, 32, 64, 3, (1, 1), 2, True),
+]
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w,k,stride,act,use_res", CASES)
+def test_conv_fprop_matches_torch(b, cin, cout, h, w, k, stride, act, use_res, cuda_lib):
+    from delora_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(cin * 131 + cout + k)
+    x = torch.randn(b, cin, h, w, device=DEV, generator=g) * 0.5
+    wt = torch.randn(cout, cin, k, k, device=DEV, generator=g) / (cin * k * k) ** 0.5
+    ho, wo = h // stride[0], w // stride[1]
+    res = torch.randn(b, cout, ho, wo, device=DEV, generator=g) * 0.5 if use_res else None
+    wn = wt.permute(0, 2, 3, 1).reshape(cout, k * k, cin).contiguous().to(torch.bfloat16)
+    y = ops.conv2d_fprop(to_padded_nhwc(x), wn, h, w, k, stride, act, to_padded_nhwc(res) if use_res else None)
+    got = ops.nhwc_to_nchw(y, ho, wo)
+    xb, wb = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    if k == 3:       # circular W padding + zero H padding: src/models/resnet_modified.py:162-168, :126-129
+        ref = F.conv2d(F.pad(xb, (1, 1, 0, 0), mode="circular"), wb, stride=stride, padding=(1, 0))
+    else:            # 1x1 downsample: :132-134
+        ref = F.conv2d(xb, wb, stride=stride)
+    if use_res:
+        ref = ref + res.to(torch.bfloat16).float()
+    ref = torch.relu(ref) if act == 1 else torch.tanh(ref) if act == 2 else ref
+    # fp32 accumulation of exact bf16 products; the output is rounded to bf16 (rel 2^-8)
+    assert (got - ref).abs().max().item() <= 6e-3 * max(1.0, ref.abs().max().item())
+    yf = y.float()
+    assert torch.equal(yf[:, 1:-1, 0], yf[:, 1:-1, wo]) and torch.equal(yf[:, 1:-1, wo + 1], yf[:, 1:-1, 1])
+    assert float(yf[:, 0].abs().max()) == 0.0 and float(yf[:, -1].abs().max()) == 0.0
+
+
+def test_conv_rejects_unsupported_shapes(cuda_lib):
+    from delora_b200 import ops
+    x = torch.zeros(1, 10, 130, 32, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(64, 9, 32, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        ops.conv2d_fprop(x, w, 8, 128, 3, (1, 1))
+
+
+def test_tensor_core_encoder_matches_torch_model(cuda_lib):
+    from delora_b200 import ops, synthetic
+    from delora_b200.models.model import OdometryModel
+    from delora_b200.models.tc_encoder import TensorCoreEncoder
+    h, w, b = 64, 512, 2
+    cfg = synthetic.fov_config(h=h, w=w, device=DEV)
+    cfg.update({"pre_feature_extraction": False, "resnet_outputs": 1000, "use_dropout": False, "layers": [2, 2, 2, 2],
+                "factor_fewer_resnet_channels": 1, "activation_fct": "tanh", "use_single_mlp_at_output": False})
+    torch.manual_seed(0)
+    model = OdometryModel(cfg).to(DEV).eval()
+    enc = TensorCoreEncoder(model)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    img1 = torch.randn(b, 4, h, w, device=DEV, generator=g) * 5.0
+    img2 = torch.randn(b, 4, h, w, device=DEV, generator=g) * 5.0
+    with torch.no_grad():
+        ref = model.forward_features(image_1=img1, image_2=img2)
+        t_ref, q_ref = model(image_1=img1, image_2=img2)
+    feats = enc.features(img1, img2)
+    for (x, fh, fw), r in zip(feats, ref[:4]):
+        got = ops.nhwc_to_nchw(x, fh, fw)
+        assert got.shape == r.shape
+        cos = F.cosine_similarity(got.flatten(), r.flatten(), dim=0).item()
+        assert cos > 0.999, cos                        # bf16 activations through up to 20 layers
+    t, q = enc.forward(img1, img2)
+    assert (t - t_ref).abs().max().item() < 2e-2 and (q - q_ref).abs().max().item() < 2e-2
+    # model-level switch: eval + no_grad routes through the tensor-core encoder
+    model.config["use_tensor_core_encoder"] = True
+    with torch.no_grad():
+        t2, q2 = model(image_1=img1, image_2=img2)
+    assert torch.equal(t2, t) and torch.equal(q2, q)
