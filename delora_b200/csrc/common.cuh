@@ -59,11 +59,94 @@ __device__ __forceinline__ float range2(float x, float y) {
     return __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
 }
 
+// ---------------------------------------------------------------------------------------------
+// atan2f with the bits of torch's CPU path.  torch.atan2 on float32 CPU tensors is SLEEF's
+// `Sleef_atan2f{8,16}_u10` (FMA builds); CUDA's libdevice atan2f differs from it by 1-2 ulp in a few
+// percent of the inputs, enough to move a point across a pixel-rounding boundary now and then.
+// This is the same algorithm operation by operation (double-float arithmetic with fma; restated
+// from SLEEF's published source and verified against this image's libtorch: see
+// oracle/sleef_atan2f.c, its scalar twin, bit-identical to Sleef_atan2f8_u10avx2 on 8e6 pairs).
+// Every operation is an IEEE round-to-nearest intrinsic so nvcc can neither fuse nor reorder.
+struct F2 { float x, y; };
+__device__ __forceinline__ F2 df_div(F2 n, F2 d) {
+    const float t = __fdiv_rn(1.0f, d.x);
+    const float s = __fmul_rn(n.x, t);
+    const float u = __fmaf_rn(t, n.x, -s);
+    const float v = __fmaf_rn(-d.y, t, __fmaf_rn(-d.x, t, 1.0f));
+    return {s, __fmaf_rn(s, v, __fmaf_rn(n.y, t, u))};
+}
+__device__ __forceinline__ F2 df_squ(F2 x) {
+    const float s = __fmul_rn(x.x, x.x);
+    return {s, __fmaf_rn(__fadd_rn(x.x, x.x), x.y, __fmaf_rn(x.x, x.x, -s))};
+}
+__device__ __forceinline__ F2 df_norm(F2 t) {
+    const float s = __fadd_rn(t.x, t.y);
+    return {s, __fadd_rn(__fsub_rn(t.x, s), t.y)};
+}
+__device__ __forceinline__ F2 df_mul(F2 x, F2 y) {
+    const float s = __fmul_rn(x.x, y.x);
+    return {s, __fmaf_rn(x.x, y.y, __fmaf_rn(x.y, y.x, __fmaf_rn(x.x, y.x, -s)))};
+}
+__device__ __forceinline__ F2 df_mul_f(F2 x, float y) {
+    const float s = __fmul_rn(x.x, y);
+    return {s, __fmaf_rn(x.y, y, __fmaf_rn(x.x, y, -s))};
+}
+__device__ __forceinline__ float mulsign(float x, float y) {
+    return __uint_as_float(__float_as_uint(x) ^ (__float_as_uint(y) & 0x80000000u));
+}
+__device__ __forceinline__ float sleef_atan2f_u10(float y0, float x0) {
+    float x = x0, y = y0;
+    if (fabsf(x) < 2.9387372783541830947e-39f) { x = __fmul_rn(x, 16777216.0f); y = __fmul_rn(y, 16777216.0f); }
+    F2 yy = {fabsf(y), 0.0f}, xx = {x, 0.0f};
+    int q = (xx.x < 0.0f) ? -2 : 0;
+    if (xx.x < 0.0f) { xx.x = -xx.x; xx.y = -xx.y; }
+    const bool p = xx.x < yy.x;
+    if (p) q += 1;
+    F2 s = p ? F2{-xx.x, -xx.y} : yy;
+    F2 t = p ? yy : xx;
+    s = df_div(s, t);
+    t = df_norm(df_squ(s));
+    float u = -0.00176397908944636583328247f;
+    u = __fmaf_rn(u, t.x, 0.0107900900766253471374512f);
+    u = __fmaf_rn(u, t.x, -0.0309564601629972457885742f);
+    u = __fmaf_rn(u, t.x, 0.0577365085482597351074219f);
+    u = __fmaf_rn(u, t.x, -0.0838950723409652709960938f);
+    u = __fmaf_rn(u, t.x, 0.109463557600975036621094f);
+    u = __fmaf_rn(u, t.x, -0.142626821994781494140625f);
+    u = __fmaf_rn(u, t.x, 0.199983194470405578613281f);
+    {   // t = t * (c + u*t.x)
+        const float c = -0.333332866430282592773438f, w = __fmul_rn(u, t.x);
+        const float ax = __fadd_rn(c, w);
+        t = df_mul(t, F2{ax, __fadd_rn(__fsub_rn(c, ax), w)});
+    }
+    {   // t = s * (1 + t)
+        const float bx = __fadd_rn(1.0f, t.x);
+        t = df_mul(s, F2{bx, __fadd_rn(__fadd_rn(__fsub_rn(1.0f, bx), t.x), t.y)});
+    }
+    {   // t = q * (pi/2 as hi+lo) + t
+        const F2 pq = df_mul_f(F2{1.5707963705062866211f, -4.3711388286737928865e-08f}, (float)q);
+        const float sx = __fadd_rn(pq.x, t.x);
+        t = F2{sx, __fadd_rn(__fadd_rn(__fadd_rn(__fsub_rn(pq.x, sx), t.x), pq.y), t.y)};
+    }
+    float r = __fadd_rn(t.x, t.y);
+    r = mulsign(r, x);
+    const float pio2 = 1.5707963267948966f, pio4 = 0.78539816339744831f, pi = 3.14159265358979323846f;
+    if (isinf(x) || x == 0.0f) r = __fsub_rn(pio2, isinf(x) ? mulsign(pio2, x) : 0.0f);
+    if (isinf(y)) r = __fsub_rn(pio2, isinf(x) ? mulsign(pio4, x) : 0.0f);
+    if (y == 0.0f) r = signbit(x) ? pi : 0.0f;
+    if (isnan(x) || isnan(y)) return __int_as_float(0x7fc00000);
+    return mulsign(r, y);
+}
+
 // (u, v) with the reference's op order: src/utility/projection.py:21-31.
+// div_mode 0: torch-CPU arithmetic (SLEEF atan2, true division) -- bit-identical to the reference's
+//             CPU tensors; div_mode 1: libdevice atan2f and a*(1/b), what torch-CUDA would compute.
 __device__ __forceinline__ void pixel_coords(const GridParams& g, float x, float y, float z,
                                              float& u, float& v) {
-    float au = __fsub_rn(atan2f(y, x), g.hf0);
-    float av = __fsub_rn(atan2f(z, range2(x, y)), g.vf0);
+    const float a_h = (g.div_mode == 0) ? sleef_atan2f_u10(y, x) : atan2f(y, x);
+    const float a_v = (g.div_mode == 0) ? sleef_atan2f_u10(z, range2(x, y)) : atan2f(z, range2(x, y));
+    float au = __fsub_rn(a_h, g.hf0);
+    float av = __fsub_rn(a_v, g.vf0);
     if (g.div_mode == 0) {
         u = __fmul_rn(__fdiv_rn(au, g.hspan), g.wm1);
         v = __fmul_rn(__fdiv_rn(av, g.vspan), g.hm1);

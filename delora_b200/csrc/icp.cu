@@ -322,7 +322,7 @@ extern "C" int delora_icp_fwd_bwd(const delora_f4* src_pts4, const delora_f4* sr
                          partials, "delora_icp_fwd_bwd: null pointer");
     DELORA_CHECK_ARG(B > 0 && B <= 65535 && src_stride > 0 && tgt_stride > 0 && H > 0 && W > 0,
                      "delora_icp_fwd_bwd: bad shape");
-    const GridParams g = make_grid(H, W, hfov0, hfov1, vfov0, vfov1, 0);
+    const GridParams g = make_grid(H, W, hfov0, hfov1, vfov0, vfov1, 1);
     const int rows = delora_icp_partial_rows(src_stride);
     const IcpScratch sc = icp_scratch(partials, B, rows);
     dim3 grid((src_stride + kIcpThreads - 1) / kIcpThreads, B);

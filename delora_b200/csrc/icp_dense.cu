@@ -216,7 +216,7 @@ extern "C" int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_
     DELORA_CHECK_ARG(src_grid && src_ngrid && T && tgt_grid && tgt_ngrid && losses && grad_T && scratch,
                      "delora_icp_dense_fwd_bwd: null pointer");
     DELORA_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0, "delora_icp_dense_fwd_bwd: bad shape");
-    const GridParams g = make_grid(H, W, hfov0, hfov1, vfov0, vfov1, 0);
+    const GridParams g = make_grid(H, W, hfov0, hfov1, vfov0, vfov1, 1);
     const int HW = H * W;
     const int rows = (HW + 31) / 32;                  // one partial row per warp of 32 source pixels
     const IcpScratch sc = icp_scratch(scratch, B, rows);

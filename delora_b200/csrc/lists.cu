@@ -291,7 +291,7 @@ extern "C" int delora_grid_build(const float* pts, const float* nrm, const int32
                                  int32_t* scratch, void* stream) {
     DELORA_CHECK_ARG(pts && n && pts4 && nrm4 && cell_start && cursor && scratch, "delora_grid_build: null pointer");
     DELORA_CHECK_ARG(B > 0 && B <= 65535 && n_stride > 0 && H > 0 && W > 0, "delora_grid_build: bad shape");
-    const GridParams g = make_grid(H, W, hfov0, hfov1, vfov0, vfov1, 0);
+    const GridParams g = make_grid(H, W, hfov0, hfov1, vfov0, vfov1, 1);
     const int HW = H * W;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)B * HW, st);

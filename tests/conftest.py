@@ -8,6 +8,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+@pytest.fixture(autouse=True, scope="session")
+def _single_thread_torch_cpu():
+    """The oracle's float coordinates are pinned with one CPU thread (see oracle/gen_golden.py: torch
+    mixes SLEEF and scalar libm per thread chunk, so (u, v) of a few tail elements depend on it)."""
+    import torch
+    torch.set_num_threads(1)
+    yield
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
 

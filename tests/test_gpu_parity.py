@@ -56,6 +56,12 @@ def check_projection(cloud, h, w, hf, vf, label, max_flip_fraction=2e-3):
     du = (u_g - uo)[fin].abs().max().item()
     dv = (v_g - vo)[fin].abs().max().item()
     assert du < 1e-3 and dv < 1e-3, (du, dv)
+    # the kernel's atan2 is SLEEF's algorithm (common.cuh `sleef_atan2f_u10`): bit-identical to torch-CPU
+    # except for the < 32 trailing elements that torch (one thread) evaluates with the scalar libm
+    mism_u = int(((u_g != uo) & fin).sum())
+    mism_v = int(((v_g != vo) & fin).sum())
+    print(f"[{label}] float (u,v) not bit-identical to torch-CPU: u {mism_u}, v {mism_v} of {cloud.shape[1]}")
+    assert mism_u <= 31 and mism_v <= 31, (mism_u, mism_v)
     flips = ((torch.round(u_g) != torch.round(uo)) | (torch.round(v_g) != torch.round(vo))) & fin
     nflip = int(flips.sum())
     fu = (uo[flips] - torch.floor(uo[flips]) - 0.5).abs()
@@ -250,7 +256,10 @@ def test_pair_pipeline_end_to_end(name, golden, cuda_lib):
     gerr = np.abs(grad_t[0].numpy().reshape(3, 4) - g_ref).max() / np.abs(g_ref).max()
     print(f"[{name}] end-to-end vs reference golden: po2pl rel={rel_pl:.2e} pl2pl rel={rel_nn:.2e} "
           f"grad_T rel(max)={gerr:.2e} pairs={int(losses[0, 3])} (ref {meta['num_pairs']})")
-    assert rel_pl < 1e-4 and rel_nn < 1e-4 and gerr < 1e-3
+    # with the SLEEF-exact atan2 the projection reproduces the CPU reference's pixels, so the whole chain
+    # meets the 1e-5 bar against the REFERENCE's own numbers (not only against the oracle on equal inputs)
+    assert int(losses[0, 3]) == meta["num_pairs"]
+    assert rel_pl < 1e-5 and rel_nn < 1e-5 and gerr < 1e-4
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -108,3 +108,39 @@ def test_quaternion_to_T(golden):
     z = np.load(os.path.join(GOLDEN, "quaternion.npz"))
     t = orc.transformation_matrix_quaternion(torch.from_numpy(z["translation"]), torch.from_numpy(z["quaternion"]))
     assert np.array_equal(t.numpy(), z["T"])
+
+
+def test_sleef_restatement_matches_torch_atan2():
+    """oracle/sleef_atan2f.c (scalar twin of the CUDA `sleef_atan2f_u10`) against torch.atan2 on CPU:
+    bit-identical wherever torch runs its vectorised (SLEEF) path, i.e. everywhere except the < 32
+    trailing elements torch hands to the scalar libm."""
+    import ctypes
+    import subprocess
+    from helpers import ROOT
+    out_dir = os.path.join(ROOT, "oracle", "_ref")
+    os.makedirs(out_dir, exist_ok=True)
+    lib = os.path.join(out_dir, "libsleef_atan2f.so")
+    subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-mfma", "-ffp-contract=off",
+                    os.path.join(ROOT, "oracle", "sleef_atan2f.c"), "-o", lib, "-lm"], check=True)
+    L = ctypes.CDLL(lib)
+    L.delora_sleef_atan2f_array.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_long]
+
+    def mine(y, x):
+        o = np.empty_like(y)
+        L.delora_sleef_atan2f_array(y.ctypes.data, x.ctypes.data, o.ctypes.data, len(y))
+        return o
+    rng = np.random.default_rng(0)
+    n = 32 * 62500                                            # multiple of 32: no scalar tail with one thread
+    for scale in (80.0, 1e-3, 1e6):
+        x = ((rng.random(n) - 0.5) * scale).astype(np.float32)
+        y = ((rng.random(n) - 0.5) * scale).astype(np.float32)
+        ref = torch.atan2(torch.from_numpy(y), torch.from_numpy(x)).numpy()
+        assert np.array_equal(mine(y, x).view(np.int32), ref.view(np.int32))
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 1e-40, -1e-40, 1e-30, 3e38, 5.0, -7.5], np.float32)
+    yy, xx = [a.ravel().copy() for a in np.meshgrid(sp, sp)]
+    pad = (-len(yy)) % 32
+    yy, xx = np.concatenate((yy, np.ones(pad, np.float32))), np.concatenate((xx, np.ones(pad, np.float32)))
+    ref = torch.atan2(torch.from_numpy(yy), torch.from_numpy(xx)).numpy()
+    assert np.array_equal(mine(yy, xx).view(np.int32), ref.view(np.int32))
+    nan = np.array([np.nan, 1.0] * 16, np.float32)
+    assert np.isnan(mine(nan, nan[::-1].copy())).all()
