@@ -125,7 +125,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // ---------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                     const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y, ConvParams p) {
+                     const __nv_bfloat16* __restrict__ residual, const __nv_bfloat16* __restrict__ saved,
+                     __nv_bfloat16* __restrict__ y, ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -236,6 +237,23 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         }
                     }
                 }
+                if (p.act >= 3) {
+                    // backward (dgrad) modes: the accumulator is dL/d(activation output); multiply by the
+                    // activation derivative evaluated on the SAVED forward output a: tanh' = 1 - a^2, relu' = [a > 0]
+                    const uint4* sp = reinterpret_cast<const uint4*>(saved + pix * p.Cout + n0 + c0);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const uint4 sv = __ldg(sp + j4);
+                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&sv);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 a = __bfloat1622float2(h[e]);
+                            const float d0 = (p.act == 3) ? fmaf(-a.x, a.x, 1.0f) : (a.x > 0.0f ? 1.0f : 0.0f);
+                            const float d1 = (p.act == 3) ? fmaf(-a.y, a.y, 1.0f) : (a.y > 0.0f ? 1.0f : 0.0f);
+                            v[j4 * 8 + e * 2] *= d0; v[j4 * 8 + e * 2 + 1] *= d1;
+                        }
+                    }
+                }
                 uint4 out[4];
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -267,6 +285,165 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.BN));
     }
+}
+
+// ---------------------------------------------------------------- weight gradient
+// dW[co][tap][ci] = sum over output pixels of dZ[pix][co] * X[pix*stride + tap][ci]
+// (autograd's backward of the reference's torch.nn.Conv2d layers, src/models/resnet_modified.py:40,:126-134).
+// GEMM with M = output channels (128 per CTA), N = input channels (64..256 per CTA), K = PIXELS: both
+// operands are pixel-major NHWC tiles (64 pixels x 64 channels, 128-byte rows, TMA SWIZZLE_128B), i.e.
+// "MN-major" for the tensor core (a_major = b_major = 1 in the instruction descriptor; descriptor
+// LBO = 8 KB between 64-channel blocks, SBO = 1 KB between groups of 8 pixel rows; one tcgen05.mma
+// consumes K = 16 pixels = 2 KB).  One CTA = one filter tap x one (co, ci) tile x one slice of the
+// pixels (split-K); each slice writes its fp32 partial, a second kernel sums the slices in a fixed
+// order (deterministic) into the torch weight layout.
+struct WgradParams {
+    int B, Hout, Wout, Cin, Cout;
+    int ksize, taps, stride_h, stride_w, pad_off;
+    int tiles_per_row;        // Wout / 64
+    int k_tiles;              // B * Hout * tiles_per_row
+    int splits;
+    int ci_tiles, nb;         // nb = 64-channel blocks of the N tile (N = 64 * nb)
+    int a_blocks;             // 2 (Cout >= 128) or 1 (Cout == 64: rows 64..127 of the tile are unused)
+    int stages;
+};
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x,
+                     float* __restrict__ partial, WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int blk_bytes = 64 * 64 * 2;                        // 64 pixels x 64 channels bf16 = 8 KB
+    const int a_bytes = 2 * blk_bytes, b_bytes = p.nb * blk_bytes;
+    const int kStages = p.stages;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * a_bytes;
+    uint64_t* full_bar = (uint64_t*)(smem_b + kStages * b_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+    uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tap = blockIdx.x;
+    const int co_tile = blockIdx.y / p.ci_tiles, ci_tile = blockIdx.y % p.ci_tiles;
+    const int split = blockIdx.z;
+    const int co0 = co_tile * 128, ci0 = ci_tile * 64 * p.nb;
+    const int r = tap / p.ksize, q = tap - r * p.ksize;
+    const int per = (p.k_tiles + p.splits - 1) / p.splits;
+    const int k_begin = split * per, k_end = min(p.k_tiles, k_begin + per);
+    const int n_iter = max(0, k_end - k_begin);
+    const int N = 64 * p.nb;
+    const uint32_t tmem_cols = N <= 64 ? 64u : (N <= 128 ? 128u : 256u);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                     "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < n_iter; ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(empty_bar + s, ph ^ 1);
+                int kt = k_begin + it;
+                const int wt = kt % p.tiles_per_row; kt /= p.tiles_per_row;
+                const int ho = kt % p.Hout;
+                const int b = kt / p.Hout;
+                mbar_expect_tx(full_bar + s, (uint32_t)(p.a_blocks * blk_bytes + b_bytes));
+                for (int j = 0; j < p.a_blocks; ++j)
+                    tma_load_4d(smem_a + s * a_bytes + j * blk_bytes, &map_dz, full_bar + s, co0 + 64 * j, wt * 64 + 1,
+                                ho + 1, b);
+                for (int j = 0; j < p.nb; ++j)
+                    tma_load_4d(smem_b + s * b_bytes + j * blk_bytes, &map_x, full_bar + s, ci0 + 64 * j,
+                                wt * 64 * p.stride_w + q + p.pad_off, ho * p.stride_h + r + p.pad_off, b);
+            }
+        }
+    } else if (warp == 1) {
+        // D = F32, A = B = BF16, both MN-major (bits 15, 16), N, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int it = 0; it < n_iter; ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(full_bar + s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                // MN-major SW128 descriptors: LBO = 8 KB (next 64-channel block), SBO = 1 KB (next 8 pixels)
+                const uint32_t a_addr = smem_u32(smem_a + s * a_bytes), b_addr = smem_u32(smem_b + s * b_bytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {                 // 64 pixels = 4 x K16
+                    uint64_t da = 0, db = 0;
+                    da |= (uint64_t)(((a_addr + k * 2048) & 0x3FFFFu) >> 4);
+                    da |= (uint64_t)(blk_bytes >> 4) << 16;
+                    da |= (uint64_t)(1024 >> 4) << 32;
+                    da |= (uint64_t)1 << 46;
+                    da |= (uint64_t)2 << 61;
+                    db |= (uint64_t)(((b_addr + k * 2048) & 0x3FFFFu) >> 4);
+                    db |= (uint64_t)(blk_bytes >> 4) << 16;
+                    db |= (uint64_t)(1024 >> 4) << 32;
+                    db |= (uint64_t)1 << 46;
+                    db |= (uint64_t)2 << 61;
+                    tcgen05_mma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                tcgen05_commit(empty_bar + s);
+                if (it == n_iter - 1) tcgen05_commit(tmem_full_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;                           // output channel row of the tile
+        const int co = co0 + m;
+        float* __restrict__ out = partial + (((size_t)split * p.taps + tap) * p.Cout + co) * p.Cin + ci0;
+        if (n_iter > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
+                if (co < p.Cout) {
+                    float4* o4 = reinterpret_cast<float4*>(out + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        o4[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                            __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        } else if (co < p.Cout) {
+            for (int c = 0; c < N; ++c) out[c] = 0.0f;
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
+// sum the split-K slices in order and write the torch layout dW[co][ci][r][s] (ci < Cin_true)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cout, int Cin, int Cin_true,
+                    float* __restrict__ dw) {
+    const size_t total = (size_t)Cout * Cin_true * taps;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin_true);
+    const int co = (int)(i / ((size_t)taps * Cin_true));
+    float acc = 0.0f;
+    for (int s = 0; s < splits; ++s) acc += partial[(((size_t)s * taps + tap) * Cout + co) * Cin + ci];
+    dw[i] = acc;
 }
 
 // ---------------------------------------------------------------- layout helpers (bandwidth kernels)
@@ -333,6 +510,32 @@ maxpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, in
     *reinterpret_cast<__nv_bfloat162*>(y + pix * C + 2 * c2) = o;
     if (wo == 0) *reinterpret_cast<__nv_bfloat162*>(y + (pix + Wout) * C + 2 * c2) = o;
     if (wo == Wout - 1) *reinterpret_cast<__nv_bfloat162*>(y + (pix - Wout) * C + 2 * c2) = o;
+}
+
+// Backward of a strided convolution = stride-1 convolution of the ZERO-UPSAMPLED output gradient with the
+// flipped filter.  x [B,H+2,W+2,C] padded -> y [B,H*sh+2,W*sw+2,C] padded: y[h*sh, w*sw] = x[h, w], zeros
+// elsewhere (incl. correct circular halo columns and zero halo rows).
+__global__ void __launch_bounds__(256)
+zero_upsample_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int sh, int sw,
+                     __nv_bfloat16* __restrict__ y) {
+    const int Ho = H * sh, Wo = W * sw, groups = C / 8;
+    const size_t total = (size_t)B * (Ho + 2) * (Wo + 2) * groups;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % groups);
+    const size_t pixel = i / groups;
+    const int wp = (int)(pixel % (Wo + 2)), hp = (int)((pixel / (Wo + 2)) % (Ho + 2));
+    const int b = (int)(pixel / ((size_t)(Wo + 2) * (Ho + 2)));
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (hp >= 1 && hp <= Ho) {
+        int w = wp - 1;                       // circular halo: padded col 0 = col Wo-1, col Wo+1 = col 0
+        if (w < 0) w = Wo - 1;
+        if (w >= Wo) w = 0;
+        const int h = hp - 1;
+        if (h % sh == 0 && w % sw == 0)
+            out = __ldg(reinterpret_cast<const uint4*>(x + ((((size_t)b * (H + 2)) + h / sh + 1) * (W + 2) + w / sw + 1) * C) + g);
+    }
+    *reinterpret_cast<uint4*>(y + pixel * C + g * 8) = out;
 }
 
 // padded NHWC bf16 -> NCHW fp32 (interior only): the reference's feature-map layout, for checks / heads
@@ -414,10 +617,11 @@ static const TensorMaps* get_maps(const void* x, const void* w, int B, int Hin, 
 
 using namespace delora;
 
-extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void* residual, void* y, int B, int Hin,
-                                        int Win, int Cin, int Cout, int ksize, int stride_h, int stride_w, int act,
-                                        void* stream) {
+extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void* residual, const void* saved, void* y,
+                                        int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride_h,
+                                        int stride_w, int act, void* stream) {
     DELORA_CHECK_ARG(x && w && y, "delora_conv2d_fprop_bf16: null pointer");
+    DELORA_CHECK_ARG(act >= 0 && act <= 4 && (act < 3 || saved), "delora_conv2d_fprop_bf16: act=%d (3/4 need `saved`)", act);
     DELORA_CHECK_ARG(ksize == 3 || ksize == 1, "delora_conv2d_fprop_bf16: kernel size %d unsupported", ksize);
     DELORA_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0, "delora_conv2d_fprop_bf16: Cin=%d, Cout=%d must be multiples of 64",
                      Cin, Cout);
@@ -448,7 +652,7 @@ extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void
     }
     dim3 grid(B * p.tiles_h * p.tiles_w, Cout / p.BN);
     conv_fprop_tc_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(
-        maps->x, maps->w, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, p);
+        maps->x, maps->w, (const __nv_bfloat16*)residual, (const __nv_bfloat16*)saved, (__nv_bfloat16*)y, p);
     DELORA_CHECK_LAUNCH("conv_fprop_tc_kernel");
     return 0;
 }
@@ -469,6 +673,94 @@ extern "C" int delora_maxpool_w_nhwc_bf16(const void* x, int B, int H, int W, in
     maxpool_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, B, H, W, C, (__nv_bfloat16*)y);
     DELORA_CHECK_LAUNCH("maxpool_nhwc_kernel");
+    return 0;
+}
+
+// split-K slices: enough CTAs for ~2 waves of the 148 SMs, at most 64 and at most one per 64-pixel tile
+static int wgrad_splits(int B, int Hout, int Wout, int Cin, int Cout, int ksize) {
+    const int nb = (Cin >= 256) ? 4 : (Cin / 64);
+    const int base_ctas = ksize * ksize * ((Cout + 127) / 128) * (Cin / (64 * nb));
+    int splits = (2 * kNumSMs + base_ctas - 1) / base_ctas;
+    splits = splits < 1 ? 1 : (splits > 64 ? 64 : splits);
+    const int k_tiles = B * Hout * (Wout / 64);
+    return splits > k_tiles ? (k_tiles > 0 ? k_tiles : 1) : splits;
+}
+
+extern "C" int64_t delora_conv2d_wgrad_scratch_floats(int B, int Hout, int Wout, int Cin, int Cout, int ksize) {
+    return (int64_t)wgrad_splits(B, Hout, Wout, Cin, Cout, ksize) * ksize * ksize * Cout * Cin;
+}
+
+extern "C" int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw, float* scratch, int B, int Hin, int Win,
+                                        int Cin, int Cin_true, int Cout, int ksize, int stride_h, int stride_w,
+                                        void* stream) {
+    DELORA_CHECK_ARG(x && dz && dw && scratch, "delora_conv2d_wgrad_bf16: null pointer");
+    DELORA_CHECK_ARG(ksize == 3 || ksize == 1, "delora_conv2d_wgrad_bf16: kernel size %d unsupported", ksize);
+    DELORA_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cin_true >= 1 && Cin_true <= Cin,
+                     "delora_conv2d_wgrad_bf16: Cin=%d, Cout=%d must be multiples of 64", Cin, Cout);
+    DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin % stride_h == 0 &&
+                         Win % stride_w == 0, "delora_conv2d_wgrad_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
+    WgradParams p;
+    p.B = B; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
+    p.stride_h = stride_h; p.stride_w = stride_w; p.pad_off = (ksize == 1) ? 1 : 0;
+    p.Hout = Hin / stride_h; p.Wout = Win / stride_w;
+    DELORA_CHECK_ARG(p.Wout % 64 == 0, "delora_conv2d_wgrad_bf16: Wout=%d must be a multiple of 64", p.Wout);
+    p.tiles_per_row = p.Wout / 64;
+    p.k_tiles = B * p.Hout * p.tiles_per_row;
+    p.nb = (Cin >= 256) ? 4 : (Cin / 64);                    // N tile = 64, 128 or 256 input channels
+    p.ci_tiles = Cin / (64 * p.nb);
+    p.a_blocks = (Cout >= 128) ? 2 : 1;
+    const int co_tiles = (Cout + 127) / 128;
+    p.splits = wgrad_splits(B, p.Hout, p.Wout, Cin, Cout, ksize);
+    p.stages = (p.nb == 4) ? 3 : 4;
+    PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode();
+    DELORA_CHECK_ARG(encode != nullptr, "delora_conv2d_wgrad_bf16: cuTensorMapEncodeTiled not available");
+    CUtensorMap map_dz, map_x;
+    {
+        const int Hp = p.Hout + 2, Wp = p.Wout + 2;
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)Wp * Cout * 2, (cuuint64_t)Hp * Wp * Cout * 2};
+        cuuint32_t box[4] = {64, 64, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult rc = encode(&map_dz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dz), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DELORA_CHECK_ARG(rc == CUDA_SUCCESS, "delora_conv2d_wgrad_bf16: tensor map (dz) failed: %d", (int)rc);
+    }
+    {
+        const int Hp = Hin + 2, Wp = Win + 2;
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Wp * Cin * 2, (cuuint64_t)Hp * Wp * Cin * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(64 * stride_w), 1, 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, 1, 1};
+        CUresult rc = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DELORA_CHECK_ARG(rc == CUDA_SUCCESS, "delora_conv2d_wgrad_bf16: tensor map (x) failed: %d", (int)rc);
+    }
+    const size_t smem = (size_t)p.stages * (2 + p.nb) * 8192 + (2 * kMaxStages + 1) * 8 + 16 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        DELORA_CHECK_ARG(e == cudaSuccess, "delora_conv2d_wgrad_bf16: smem opt-in failed: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(p.taps, co_tiles * p.ci_tiles, p.splits);
+    conv_wgrad_tc_kernel<<<grid, kConvThreads, smem, st>>>(map_dz, map_x, scratch, p);
+    DELORA_CHECK_LAUNCH("conv_wgrad_tc_kernel");
+    const size_t total = (size_t)Cout * Cin_true * p.taps;
+    wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(scratch, p.splits, p.taps, Cout, Cin, Cin_true, dw);
+    DELORA_CHECK_LAUNCH("wgrad_reduce_kernel");
+    return 0;
+}
+
+extern "C" int delora_zero_upsample_nhwc_bf16(const void* x, int B, int H, int W, int C, int sh, int sw, void* y,
+                                              void* stream) {
+    DELORA_CHECK_ARG(x && y && C % 8 == 0 && sh >= 1 && sw >= 1, "delora_zero_upsample_nhwc_bf16: bad argument");
+    const size_t total = (size_t)B * (H * sh + 2) * (W * sw + 2) * (C / 8);
+    zero_upsample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, B, H, W, C, sh, sw, (__nv_bfloat16*)y);
+    DELORA_CHECK_LAUNCH("zero_upsample_kernel");
     return 0;
 }
 

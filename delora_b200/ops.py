@@ -251,7 +251,7 @@ def quat_to_T_bwd(quaternion, grad_t):
 
 # ---------------------------------------------------------------------------------------------
 # encoder (tcgen05 implicit-GEMM convolutions, bf16 NHWC with materialised padding)
-ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_TANH_BWD, ACT_RELU_BWD = 0, 1, 2, 3, 4
 
 
 def padded_nhwc_zeros(b, h, w, c, device):
@@ -259,7 +259,7 @@ def padded_nhwc_zeros(b, h, w, c, device):
     return torch.zeros((b, h + 2, w + 2, c), dtype=torch.bfloat16, device=device)
 
 
-def conv2d_fprop(x, weight, hin, win, ksize, stride, act=ACT_NONE, residual=None, out=None):
+def conv2d_fprop(x, weight, hin, win, ksize, stride, act=ACT_NONE, residual=None, out=None, saved=None):
     """x [B,Hin+2,Win+2,Cin] bf16 padded NHWC, weight [Cout,k*k,Cin] bf16 -> y [B,Hout+2,Wout+2,Cout]."""
     b, _, _, cin = x.shape
     cout = weight.shape[0]
@@ -269,8 +269,43 @@ def conv2d_fprop(x, weight, hin, win, ksize, stride, act=ACT_NONE, residual=None
     L = _lib.lib()
     _lib.check(L.delora_conv2d_fprop_bf16(_req(x, torch.bfloat16, "x"), _req(weight, torch.bfloat16, "weight"),
                                           _req(residual, torch.bfloat16, "residual") if residual is not None else None,
+                                          _req(saved, torch.bfloat16, "saved") if saved is not None else None,
                                           out.data_ptr(), b, hin, win, cin, cout, ksize, stride[0], stride[1], int(act),
                                           _stream()), "delora_conv2d_fprop_bf16")
+    return out
+
+
+_wgrad_scratch = {}
+
+
+def conv2d_wgrad(x, dz, hin, win, ksize, stride, cin_true=None):
+    """x [B,Hin+2,Win+2,Cin], dz [B,Hout+2,Wout+2,Cout] (bf16 padded NHWC) -> dW [Cout,Cin_true,k,k] fp32."""
+    b, _, _, cin = x.shape
+    cout = dz.shape[3]
+    cin_true = cin if cin_true is None else int(cin_true)
+    hout, wout = hin // stride[0], win // stride[1]
+    L = _lib.lib()
+    n = int(L.delora_conv2d_wgrad_scratch_floats(b, hout, wout, cin, cout, ksize))
+    key = (x.device.index, n)
+    scratch = _wgrad_scratch.get(key)
+    if scratch is None:
+        scratch = torch.empty((n,), dtype=torch.float32, device=x.device)
+        _wgrad_scratch[key] = scratch
+    dw = torch.empty((cout, cin_true, ksize, ksize), dtype=torch.float32, device=x.device)
+    _lib.check(L.delora_conv2d_wgrad_bf16(_req(x, torch.bfloat16, "x"), _req(dz, torch.bfloat16, "dz"), dw.data_ptr(),
+                                          scratch.data_ptr(), b, hin, win, cin, cin_true, cout, ksize, stride[0],
+                                          stride[1], _stream()), "delora_conv2d_wgrad_bf16")
+    return dw
+
+
+def zero_upsample(x, h, w, stride, out=None):
+    """x [B,H+2,W+2,C] -> [B,H*sh+2,W*sw+2,C]: x at the strided positions, zero elsewhere."""
+    b, _, _, c = x.shape
+    if out is None:
+        out = torch.empty((b, h * stride[0] + 2, w * stride[1] + 2, c), dtype=torch.bfloat16, device=x.device)
+    L = _lib.lib()
+    _lib.check(L.delora_zero_upsample_nhwc_bf16(_req(x, torch.bfloat16, "x"), b, h, w, c, stride[0], stride[1],
+                                                out.data_ptr(), _stream()), "delora_zero_upsample_nhwc_bf16")
     return out
 
 

@@ -220,10 +220,24 @@ int delora_icp_point_grads(const delora_f4* point_dir, const delora_f4* normal_d
  * residual [B, Hout+2, Wout+2, Cout] bf16 or NULL, added before the activation
  * y        [B, Hout+2, Wout+2, Cout] bf16 out (interior + circular halo columns are written; the
  *          zero halo rows must have been zeroed once by the caller)
- * ksize 3 (pad 1 in H, wrap in W) or 1 (no padding); stride_h/w in {1,2}; act: 0 none, 1 relu, 2 tanh.
+ * saved    [B, Hout+2, Wout+2, Cout] bf16 or NULL: forward activation output for the backward modes
+ * ksize 3 (pad 1 in H, wrap in W) or 1 (no padding); stride_h/w in {1,2};
+ * act: 0 none, 1 relu, 2 tanh (forward);  3 / 4: multiply (acc + residual) by tanh'(saved) = 1 - saved^2 /
+ *      relu'(saved) -- the data-gradient pass: dgrad of a stride-1 conv is this same kernel run on the output
+ *      gradient with the flipped, transposed filter (strided convs: on the zero-upsampled gradient).
  * Cin, Cout multiples of 64 (the 8-channel stem input is channel-padded by delora_images_to_nhwc_bf16). */
-int delora_conv2d_fprop_bf16(const void* x, const void* w, const void* residual, void* y, int B, int Hin, int Win,
-                             int Cin, int Cout, int ksize, int stride_h, int stride_w, int act, void* stream);
+int delora_conv2d_fprop_bf16(const void* x, const void* w, const void* residual, const void* saved, void* y, int B,
+                             int Hin, int Win, int Cin, int Cout, int ksize, int stride_h, int stride_w, int act,
+                             void* stream);
+/* Weight gradient of the same convolution on tcgen05 (split-K over pixels, deterministic reduction):
+ * x [B,Hin+2,Win+2,Cin] padded NHWC bf16 (the layer input), dz [B,Hout+2,Wout+2,Cout] padded NHWC bf16
+ * (gradient w.r.t. the pre-activation output) -> dw [Cout, Cin_true, k, k] fp32 (torch layout; Cin_true <= Cin
+ * for the channel-padded stem).  scratch: fp32 [delora_conv2d_wgrad_scratch_floats(...)].  Wout % 64 == 0. */
+int64_t delora_conv2d_wgrad_scratch_floats(int B, int Hout, int Wout, int Cin, int Cout, int ksize);
+int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw, float* scratch, int B, int Hin, int Win,
+                             int Cin, int Cin_true, int Cout, int ksize, int stride_h, int stride_w, void* stream);
+/* y[h*sh, w*sw] = x[h, w], zero elsewhere (padded NHWC bf16 in and out): input of the dgrad of strided convs */
+int delora_zero_upsample_nhwc_bf16(const void* x, int B, int H, int W, int C, int sh, int sw, void* y, void* stream);
 
 /* cat(image_1, image_2) ([B,4,H,W] fp32 each, src/models/model.py:98) -> [B,H+2,W+2,Cpad] bf16 padded NHWC */
 int delora_images_to_nhwc_bf16(const float* image_1, const float* image_2, int B, int H, int W, int Cpad,
