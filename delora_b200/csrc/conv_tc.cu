@@ -300,8 +300,10 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 struct WgradParams {
     int B, Hout, Wout, Cin, Cout;
     int ksize, taps, stride_h, stride_w, pad_off;
-    int tiles_per_row;        // Wout / 64
-    int k_tiles;              // B * Hout * tiles_per_row
+    int TW, TH;               // a K tile = TW x TH = 64 output pixels
+    int tiles_per_row;        // Wout / TW
+    int row_tiles;            // Hout / TH
+    int k_tiles;              // B * row_tiles * tiles_per_row
     int splits;
     int ci_tiles, nb;         // nb = 64-channel blocks of the N tile (N = 64 * nb)
     int a_blocks;             // 2 (Cout >= 128) or 1 (Cout == 64: rows 64..127 of the tile are unused)
@@ -358,15 +360,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_co
                 mbar_wait(empty_bar + s, ph ^ 1);
                 int kt = k_begin + it;
                 const int wt = kt % p.tiles_per_row; kt /= p.tiles_per_row;
-                const int ho = kt % p.Hout;
-                const int b = kt / p.Hout;
+                const int ho = (kt % p.row_tiles) * p.TH;
+                const int b = kt / p.row_tiles;
                 mbar_expect_tx(full_bar + s, (uint32_t)(p.a_blocks * blk_bytes + b_bytes));
                 for (int j = 0; j < p.a_blocks; ++j)
-                    tma_load_4d(smem_a + s * a_bytes + j * blk_bytes, &map_dz, full_bar + s, co0 + 64 * j, wt * 64 + 1,
+                    tma_load_4d(smem_a + s * a_bytes + j * blk_bytes, &map_dz, full_bar + s, co0 + 64 * j, wt * p.TW + 1,
                                 ho + 1, b);
                 for (int j = 0; j < p.nb; ++j)
                     tma_load_4d(smem_b + s * b_bytes + j * blk_bytes, &map_x, full_bar + s, ci0 + 64 * j,
-                                wt * 64 * p.stride_w + q + p.pad_off, ho * p.stride_h + r + p.pad_off, b);
+                                wt * p.TW * p.stride_w + q + p.pad_off, ho * p.stride_h + r + p.pad_off, b);
             }
         }
     } else if (warp == 1) {
@@ -538,6 +540,109 @@ zero_upsample_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, i
     *reinterpret_cast<uint4*>(y + pixel * C + g * 8) = out;
 }
 
+// Max-pool with argmax (training): same window as maxpool_nhwc_kernel, additionally stores which of the 9
+// window positions won (first maximum in (row, column) scan order, as PyTorch's backward assumes).
+__global__ void __launch_bounds__(256)
+maxpool_idx_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, __nv_bfloat16* __restrict__ y,
+                        uint8_t* __restrict__ idx) {
+    const int Wout = W / 2;
+    const size_t total = (size_t)B * H * Wout * C;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int wo = (int)(r % Wout); r /= Wout;
+    const int ho = (int)(r % H);
+    const int b = (int)(r / H);
+    const int Wp = W + 2, Hp = H + 2, Wpo = Wout + 2;
+    float m = -INFINITY;
+    int arg = 4;
+    for (int dr = 0; dr < 3; ++dr) {
+        const int h = ho + dr - 1;
+        if (h < 0 || h >= H) continue;
+        for (int dq = 0; dq < 3; ++dq) {
+            const float v = __bfloat162float(x[(((size_t)b * Hp + h + 1) * Wp + 2 * wo + dq) * C + c]);
+            if (v > m) { m = v; arg = dr * 3 + dq; }
+        }
+    }
+    const __nv_bfloat16 o = __float2bfloat16_rn(m);
+    const size_t pix = ((size_t)b * Hp + ho + 1) * Wpo + wo + 1;
+    y[pix * C + c] = o;
+    if (wo == 0) y[(pix + Wout) * C + c] = o;
+    if (wo == Wout - 1) y[(pix - Wout) * C + c] = o;
+    idx[i] = (uint8_t)arg;
+}
+
+// Backward of that pool fused with the derivative of the activation that produced its input:
+// dz[b,h,w,c] = act'(a[b,h,w,c]) * sum of dy over the (<= 6) windows whose argmax is (h, w).
+// w is an UNPADDED input column; the windows see the circularly padded row, so padded column 0 / W+1
+// alias columns W-1 / 0.  Output dz is padded NHWC with halo (it feeds the stem's wgrad).
+__global__ void __launch_bounds__(256)
+maxpool_bwd_act_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                       const __nv_bfloat16* __restrict__ a, int B, int H, int W, int C, int act,
+                       __nv_bfloat16* __restrict__ dz) {
+    const int Wout = W / 2;
+    const size_t total = (size_t)B * H * W * C;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+    const int Wp = W + 2, Hp = H + 2, Wpo = Wout + 2;
+    float g = 0.0f;
+    // padded columns that hold this input column: w+1 always; 0 if w == W-1; W+1 if w == 0
+    for (int alias = 0; alias < 3; ++alias) {
+        int wp;
+        if (alias == 0) wp = w + 1;
+        else if (alias == 1) { if (w != W - 1) continue; wp = 0; }
+        else { if (w != 0) continue; wp = W + 1; }
+        for (int dq = 0; dq < 3; ++dq) {                 // window column offset: wp = 2*wo + dq
+            const int t = wp - dq;
+            if (t < 0 || (t & 1)) continue;
+            const int wo = t >> 1;
+            if (wo >= Wout) continue;
+            for (int dr = 0; dr < 3; ++dr) {             // window row offset: h = ho + dr - 1
+                const int ho = h - dr + 1;
+                if (ho < 0 || ho >= H) continue;
+                const size_t o = (((size_t)b * H + ho) * Wout + wo) * C + c;
+                if (idx[o] == dr * 3 + dq)
+                    g += __bfloat162float(dy[(((size_t)b * Hp + ho + 1) * Wpo + wo + 1) * C + c]);
+            }
+        }
+    }
+    const float av = __bfloat162float(a[(((size_t)b * Hp + h + 1) * Wp + w + 1) * C + c]);
+    const float d = (act == 2) ? fmaf(-av, av, 1.0f) : (act == 1 ? (av > 0.0f ? 1.0f : 0.0f) : 1.0f);
+    const __nv_bfloat16 o = __float2bfloat16_rn(g * d);
+    const size_t pix = ((size_t)b * Hp + h + 1) * Wp + w + 1;
+    dz[pix * C + c] = o;
+    if (w == 0) dz[(pix + W) * C + c] = o;
+    if (w == W - 1) dz[(pix - W) * C + c] = o;
+}
+
+// Backward of AdaptiveAvgPool2d((1,1)) fused with the derivative of the last block's activation:
+// dz[b,h,w,c] = g[b,c] / (H*W) * act'(a[b,h,w,c]), padded NHWC with halo.
+__global__ void __launch_bounds__(256)
+avgpool_bwd_act_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ a, int B, int H, int W, int C,
+                       int act, __nv_bfloat16* __restrict__ dz) {
+    const size_t total = (size_t)B * H * W * C;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+    const size_t pix = ((size_t)b * (H + 2) + h + 1) * (W + 2) + w + 1;
+    const float av = __bfloat162float(a[pix * C + c]);
+    const float d = (act == 2) ? fmaf(-av, av, 1.0f) : (act == 1 ? (av > 0.0f ? 1.0f : 0.0f) : 1.0f);
+    const __nv_bfloat16 o = __float2bfloat16_rn(g[(size_t)b * C + c] / (float)(H * W) * d);
+    dz[pix * C + c] = o;
+    if (w == 0) dz[(pix + W) * C + c] = o;
+    if (w == W - 1) dz[(pix - W) * C + c] = o;
+}
+
 // padded NHWC bf16 -> NCHW fp32 (interior only): the reference's feature-map layout, for checks / heads
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, float* __restrict__ y) {
@@ -682,7 +787,7 @@ static int wgrad_splits(int B, int Hout, int Wout, int Cin, int Cout, int ksize)
     const int base_ctas = ksize * ksize * ((Cout + 127) / 128) * (Cin / (64 * nb));
     int splits = (2 * kNumSMs + base_ctas - 1) / base_ctas;
     splits = splits < 1 ? 1 : (splits > 64 ? 64 : splits);
-    const int k_tiles = B * Hout * (Wout / 64);
+    const int k_tiles = (B * Hout * Wout) / 64;
     return splits > k_tiles ? (k_tiles > 0 ? k_tiles : 1) : splits;
 }
 
@@ -703,9 +808,13 @@ extern "C" int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw
     p.B = B; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
     p.stride_h = stride_h; p.stride_w = stride_w; p.pad_off = (ksize == 1) ? 1 : 0;
     p.Hout = Hin / stride_h; p.Wout = Win / stride_w;
-    DELORA_CHECK_ARG(p.Wout % 64 == 0, "delora_conv2d_wgrad_bf16: Wout=%d must be a multiple of 64", p.Wout);
-    p.tiles_per_row = p.Wout / 64;
-    p.k_tiles = B * p.Hout * p.tiles_per_row;
+    p.TW = p.Wout >= 64 ? 64 : p.Wout;
+    DELORA_CHECK_ARG(64 % p.TW == 0 && p.Wout % p.TW == 0 && p.Hout % (64 / p.TW) == 0,
+                     "delora_conv2d_wgrad_bf16: output %dx%d does not tile into 64-pixel blocks", p.Hout, p.Wout);
+    p.TH = 64 / p.TW;
+    p.tiles_per_row = p.Wout / p.TW;
+    p.row_tiles = p.Hout / p.TH;
+    p.k_tiles = B * p.row_tiles * p.tiles_per_row;
     p.nb = (Cin >= 256) ? 4 : (Cin / 64);                    // N tile = 64, 128 or 256 input channels
     p.ci_tiles = Cin / (64 * p.nb);
     p.a_blocks = (Cout >= 128) ? 2 : 1;
@@ -719,7 +828,7 @@ extern "C" int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw
         const int Hp = p.Hout + 2, Wp = p.Wout + 2;
         cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)Wp * Cout * 2, (cuuint64_t)Hp * Wp * Cout * 2};
-        cuuint32_t box[4] = {64, 64, 1, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult rc = encode(&map_dz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dz), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -730,8 +839,8 @@ extern "C" int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw
         const int Hp = Hin + 2, Wp = Win + 2;
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Wp * Cin * 2, (cuuint64_t)Hp * Wp * Cin * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)(64 * stride_w), 1, 1};
-        cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, 1, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)(p.TW * stride_w), (cuuint32_t)(p.TH * stride_h), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
         CUresult rc = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -761,6 +870,35 @@ extern "C" int delora_zero_upsample_nhwc_bf16(const void* x, int B, int H, int W
     zero_upsample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, B, H, W, C, sh, sw, (__nv_bfloat16*)y);
     DELORA_CHECK_LAUNCH("zero_upsample_kernel");
+    return 0;
+}
+
+extern "C" int delora_maxpool_w_idx_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* idx, void* stream) {
+    DELORA_CHECK_ARG(x && y && idx && W % 2 == 0, "delora_maxpool_w_idx_nhwc_bf16: bad argument");
+    const size_t total = (size_t)B * H * (W / 2) * C;
+    maxpool_idx_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, B, H, W, C, (__nv_bfloat16*)y, (uint8_t*)idx);
+    DELORA_CHECK_LAUNCH("maxpool_idx_nhwc_kernel");
+    return 0;
+}
+
+extern "C" int delora_maxpool_w_bwd_nhwc_bf16(const void* dy, const void* idx, const void* a, int B, int H, int W, int C,
+                                              int act, void* dz, void* stream) {
+    DELORA_CHECK_ARG(dy && idx && a && dz && W % 2 == 0, "delora_maxpool_w_bwd_nhwc_bf16: bad argument");
+    const size_t total = (size_t)B * H * W * C;
+    maxpool_bwd_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, (const uint8_t*)idx, (const __nv_bfloat16*)a, B, H, W, C, act, (__nv_bfloat16*)dz);
+    DELORA_CHECK_LAUNCH("maxpool_bwd_act_kernel");
+    return 0;
+}
+
+extern "C" int delora_avgpool_bwd_nhwc_bf16(const float* g, const void* a, int B, int H, int W, int C, int act, void* dz,
+                                            void* stream) {
+    DELORA_CHECK_ARG(g && a && dz, "delora_avgpool_bwd_nhwc_bf16: null pointer");
+    const size_t total = (size_t)B * H * W * C;
+    avgpool_bwd_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        g, (const __nv_bfloat16*)a, B, H, W, C, act, (__nv_bfloat16*)dz);
+    DELORA_CHECK_LAUNCH("avgpool_bwd_act_kernel");
     return 0;
 }
 

@@ -25,6 +25,32 @@ def _prep(weight, cin_pad=None):
     return w.contiguous().to(torch.bfloat16)
 
 
+def _prep_flip(weight):
+    """Filter of the data-gradient convolution: [Cout,Cin,k,k] -> [Cin, k*k (flipped), Cout] bf16."""
+    cout, cin, k, _ = weight.shape
+    return weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k, cout).contiguous().to(torch.bfloat16)
+
+
+class _EncoderTrainFn(torch.autograd.Function):
+    """Differentiable encoder trunk on the tcgen05 kernels: images -> pooled [B, C4] features.
+    forward = TensorCoreEncoder chain with the activations kept; backward = per BasicBlock (reverse order)
+    wgrad(conv2), dgrad(conv2) * act'(t1), wgrad(conv1), [wgrad + dgrad of the 1x1 downsample],
+    dgrad(conv1) + identity path, * act'(block input); then max-pool and stem.  The gradients w.r.t. the
+    images are not needed (the range images are data)."""
+
+    @staticmethod
+    def forward(ctx, enc, image_1, image_2, *weights):
+        ctx.enc = enc
+        ctx.state = enc._forward_saving(image_1, image_2, weights)
+        return ctx.state["pooled"]
+
+    @staticmethod
+    def backward(ctx, g_pooled):
+        grads = ctx.enc._backward(ctx.state, g_pooled.float().contiguous())
+        ctx.state = None
+        return (None, None, None) + tuple(grads)
+
+
 class TensorCoreEncoder:
     def __init__(self, model):
         self.model = model
@@ -98,3 +124,114 @@ class TensorCoreEncoder:
         else:
             rot, trans = m.fully_connected_rotation(out), m.fully_connected_translation(out)
         return trans, rot / torch.norm(rot)
+
+    # ------------------------------------------------------------------------------------------
+    # training path (forward keeps activations, backward runs dgrad / wgrad on the tensor cores)
+    def trunk_parameters(self):
+        """Conv weights in the fixed order used by the autograd function."""
+        r = self.model.resnet
+        params = [r.conv1.weight]
+        for li in range(1, 5):
+            for blk in getattr(r, f"layer{li}"):
+                params += [blk.conv1.weight, blk.conv2.weight]
+                if blk.downsample is not None:
+                    params.append(blk.downsample[0].weight)
+        return params
+
+    def pooled_features(self, image_1, image_2):
+        """[B, C4] average-pooled encoder features with autograd through the tcgen05 kernels."""
+        return _EncoderTrainFn.apply(self, image_1.float().contiguous(), image_2.float().contiguous(),
+                                     *self.trunk_parameters())
+
+    def _forward_saving(self, image_1, image_2, weights):
+        b, _, h, w = image_1.shape
+        dev = image_1.device
+        L = ops._lib.lib()
+        it = iter(weights)
+        st = {"B": b, "H": h, "W": w, "blocks": []}
+        w_stem = next(it)
+        st["x_in"] = ops.images_to_nhwc(image_1, image_2, 64)
+        w2 = w // 2
+        st["y0"] = ops.conv2d_fprop(st["x_in"], _prep(w_stem, 64), h, w, 3, (1, 2), self.act, None,
+                                    self._buffer("t_stem", b, h, w2, 64, dev))
+        w4 = w2 // 2
+        st["p0"] = self._buffer("t_pool", b, h, w4, 64, dev)
+        st["idx"] = torch.empty((b, h, w4, 64), dtype=torch.uint8, device=dev)
+        ops._lib.check(L.delora_maxpool_w_idx_nhwc_bf16(st["y0"].data_ptr(), b, h, w2, 64, st["p0"].data_ptr(),
+                                                        st["idx"].data_ptr(), ops._stream()),
+                       "delora_maxpool_w_idx_nhwc_bf16")
+        cur, ch, cw = st["p0"], h, w4
+        for i, blk in enumerate(self.blocks):
+            w1, wc2 = next(it), next(it)
+            wd = next(it) if blk["wd"] is not None else None
+            sh, sw = blk["stride"]
+            oh, ow, co = ch // sh, cw // sw, blk["cout"]
+            t1 = ops.conv2d_fprop(cur, _prep(w1), ch, cw, 3, (sh, sw), self.act, None,
+                                  self._buffer(f"t{i}a", b, oh, ow, co, dev))
+            if wd is not None:
+                ident = ops.conv2d_fprop(cur, _prep(wd), ch, cw, 1, (sh, sw), ops.ACT_NONE, None,
+                                         self._buffer(f"t{i}d", b, oh, ow, co, dev))
+            else:
+                ident = cur
+            out = ops.conv2d_fprop(t1, _prep(wc2), oh, ow, 3, (1, 1), self.act, ident,
+                                   self._buffer(f"t{i}o", b, oh, ow, co, dev))
+            st["blocks"].append({"x": cur, "t1": t1, "out": out, "w1": w1, "w2": wc2, "wd": wd, "stride": (sh, sw),
+                                 "in_hw": (ch, cw), "out_hw": (oh, ow)})
+            cur, ch, cw = out, oh, ow
+        st["w_stem"] = w_stem
+        st["pooled"] = cur[:, 1:ch + 1, 1:cw + 1, :].float().mean(dim=(1, 2))
+        return st
+
+    def _backward(self, st, g_pooled):
+        b = st["B"]
+        dev = g_pooled.device
+        L = ops._lib.lib()
+        act_id = 1 if self.act == ops.ACT_RELU else 2
+        act_bwd = ops.ACT_RELU_BWD if self.act == ops.ACT_RELU else ops.ACT_TANH_BWD
+        blocks = st["blocks"]
+        last = blocks[-1]
+        oh, ow = last["out_hw"]
+        c_last = last["out"].shape[3]
+        dz2 = self._buffer("g_last", b, oh, ow, c_last, dev)
+        ops._lib.check(L.delora_avgpool_bwd_nhwc_bf16(g_pooled.data_ptr(), last["out"].data_ptr(), b, oh, ow, c_last,
+                                                      act_id, dz2.data_ptr(), ops._stream()),
+                       "delora_avgpool_bwd_nhwc_bf16")
+        grads_rev = []
+        d_pool = None
+        for i in range(len(blocks) - 1, -1, -1):
+            blk = blocks[i]
+            (ch, cw), (oh, ow), (sh, sw) = blk["in_hw"], blk["out_hw"], blk["stride"]
+            cin, cout = blk["x"].shape[3], blk["out"].shape[3]
+            g_w2 = ops.conv2d_wgrad(blk["t1"], dz2, oh, ow, 3, (1, 1))
+            dz1 = ops.conv2d_fprop(dz2, _prep_flip(blk["w2"]), oh, ow, 3, (1, 1), act_bwd, None,
+                                   self._buffer(f"g{i}a", b, oh, ow, cout, dev), saved=blk["t1"])
+            g_w1 = ops.conv2d_wgrad(blk["x"], dz1, ch, cw, 3, (sh, sw))
+            g_wd = None
+            if blk["wd"] is not None:
+                g_wd = ops.conv2d_wgrad(blk["x"], dz2, ch, cw, 1, (sh, sw))
+                up2 = ops.zero_upsample(dz2, oh, ow, (sh, sw), self._buffer(f"g{i}u2", b, ch, cw, cout, dev))
+                resid = ops.conv2d_fprop(up2, _prep_flip(blk["wd"]), ch, cw, 1, (1, 1), ops.ACT_NONE, None,
+                                         self._buffer(f"g{i}d", b, ch, cw, cin, dev))
+                src = ops.zero_upsample(dz1, oh, ow, (sh, sw), self._buffer(f"g{i}u1", b, ch, cw, cout, dev))
+            else:
+                resid, src = dz2, dz1
+            if i > 0:     # the block input is the previous block's activation output: fold act' into the epilogue
+                dz2 = ops.conv2d_fprop(src, _prep_flip(blk["w1"]), ch, cw, 3, (1, 1), act_bwd, resid,
+                                       self._buffer(f"g{i}x", b, ch, cw, cin, dev), saved=blk["x"])
+            else:         # the first block reads the max-pool output
+                d_pool = ops.conv2d_fprop(src, _prep_flip(blk["w1"]), ch, cw, 3, (1, 1), ops.ACT_NONE, resid,
+                                          self._buffer("g_pool", b, ch, cw, cin, dev))
+            grads_rev.append((g_w1, g_w2, g_wd))
+        h, w = st["H"], st["W"]
+        w2 = w // 2
+        dz0 = self._buffer("g_stem", b, h, w2, 64, dev)
+        ops._lib.check(L.delora_maxpool_w_bwd_nhwc_bf16(d_pool.data_ptr(), st["idx"].data_ptr(), st["y0"].data_ptr(), b, h,
+                                                        w2, 64, act_id, dz0.data_ptr(), ops._stream()),
+                       "delora_maxpool_w_bwd_nhwc_bf16")
+        g_stem = ops.conv2d_wgrad(st["x_in"], dz0, h, w, 3, (1, 2), cin_true=st["w_stem"].shape[1])
+        grads = [g_stem]
+        for g_w1, g_w2, g_wd in reversed(grads_rev):
+            grads += [g_w1, g_w2]
+            if g_wd is not None:
+                grads.append(g_wd)
+        return grads

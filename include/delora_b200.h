@@ -244,6 +244,14 @@ int delora_images_to_nhwc_bf16(const float* image_1, const float* image_2, int B
                                void* x, void* stream);
 /* MaxPool2d(3, stride (1,2), padding (1,0)) on the W-wrapped input (src/models/resnet_modified.py:46,:100-101) */
 int delora_maxpool_w_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* stream);
+/* training variants of the pools: forward with argmax (idx: uint8 [B,H,W/2,C]); backward of the max-pool
+ * fused with act'(a) of the stem activation a; backward of the global average pool fused with act'(a) of
+ * the last block (g: [B,C] fp32).  act: 0 none, 1 relu, 2 tanh.  All tensors padded NHWC bf16. */
+int delora_maxpool_w_idx_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* idx, void* stream);
+int delora_maxpool_w_bwd_nhwc_bf16(const void* dy, const void* idx, const void* a, int B, int H, int W, int C, int act,
+                                   void* dz, void* stream);
+int delora_avgpool_bwd_nhwc_bf16(const float* g, const void* a, int B, int H, int W, int C, int act, void* dz,
+                                 void* stream);
 /* padded NHWC bf16 -> NCHW fp32 (interior), the reference's feature-map layout */
 int delora_nhwc_to_nchw_f32(const void* x, int B, int H, int W, int C, float* y, void* stream);
 
