@@ -56,12 +56,13 @@ class OdometryModel(torch.nn.Module):
         return self.resnet(x)
 
     def _tensor_core_path(self):
-        """Inference (eval mode, no grad) can run the encoder on the tcgen05 convolution kernels
-        (`models/tc_encoder.py`); training keeps the differentiable torch path until the dgrad / wgrad
-        kernels exist.  Opt-in with config["use_tensor_core_encoder"] = True."""
-        if not self.config.get("use_tensor_core_encoder", False) or self.training or torch.is_grad_enabled():
+        """The encoder trunk on the tcgen05 kernels (`models/tc_encoder.py`): bf16 NHWC activations,
+        forward and (autograd) backward — fprop, dgrad and wgrad all on the tensor cores.
+        Opt-in with config["use_tensor_core_encoder"] = True; needs the full-width model
+        (factor_fewer_resnet_channels == 1), no dropout and no pre-feature extractor."""
+        if not self.config.get("use_tensor_core_encoder", False):
             return None
-        if self.pre_feature_extraction or self.config["factor_fewer_resnet_channels"] != 1:
+        if self.pre_feature_extraction or self.config["factor_fewer_resnet_channels"] != 1 or self.config["use_dropout"]:
             return None
         if getattr(self, "_tc_encoder", None) is None:
             from . import tc_encoder
@@ -70,9 +71,12 @@ class OdometryModel(torch.nn.Module):
 
     def forward(self, image_1, image_2):
         tc = self._tensor_core_path()
-        if tc is not None:
+        if tc is not None and not torch.is_grad_enabled():
             return tc.forward(image_1.contiguous(), image_2.contiguous())
-        x = self.forward_features(image_1=image_1, image_2=image_2)[-1]
+        if tc is not None:
+            x = self.resnet.fc(tc.pooled_features(image_1, image_2))        # differentiable tcgen05 trunk
+        else:
+            x = self.forward_features(image_1=image_1, image_2=image_2)[-1]
         if self.config["use_single_mlp_at_output"]:
             x = self.fully_connected_rot_trans(x)
             x_rotation, x_translation = x[:, :4], x[:, 4:]

@@ -84,8 +84,70 @@ def test_tensor_core_encoder_matches_torch_model(cuda_lib):
         assert cos > 0.999, cos                        # bf16 activations through up to 20 layers
     t, q = enc.forward(img1, img2)
     assert (t - t_ref).abs().max().item() < 2e-2 and (q - q_ref).abs().max().item() < 2e-2
-    # model-level switch: eval + no_grad routes through the tensor-core encoder
+    # model-level switch: no_grad routes through the tensor-core encoder
     model.config["use_tensor_core_encoder"] = True
     with torch.no_grad():
         t2, q2 = model(image_1=img1, image_2=img2)
     assert torch.equal(t2, t) and torch.equal(q2, q)
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w,k,stride", [
+    (2, 64, 64, 8, 128, 3, (1, 1)), (2, 64, 128, 16, 256, 3, (1, 2)), (2, 64, 128, 16, 256, 1, (1, 2)),
+    (2, 256, 512, 16, 128, 3, (2, 2)), (2, 256, 512, 16, 128, 1, (2, 2)), (1, 512, 512, 32, 64, 3, (1, 1)),
+    (1, 512, 512, 8, 16, 3, (1, 1))])
+def test_conv_dgrad_wgrad_match_autograd(b, cin, cout, h, w, k, stride, cuda_lib):
+    """Backward of the convolution: wgrad kernel and dgrad (= fprop kernel on the zero-upsampled output
+    gradient with the flipped filter) against torch autograd on bf16-rounded operands."""
+    from delora_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(cin + 7 * cout + k)
+    x = (torch.randn(b, cin, h, w, device=DEV, generator=g) * 0.5).to(torch.bfloat16).float().requires_grad_(True)
+    wt = (torch.randn(cout, cin, k, k, device=DEV, generator=g) / (cin * k * k) ** 0.5).to(torch.bfloat16).float()
+    wt.requires_grad_(True)
+    ho, wo = h // stride[0], w // stride[1]
+    dz = (torch.randn(b, cout, ho, wo, device=DEV, generator=g) * 0.5).to(torch.bfloat16).float()
+    if k == 3:
+        y = F.conv2d(F.pad(x, (1, 1, 0, 0), mode="circular"), wt, stride=stride, padding=(1, 0))
+    else:
+        y = F.conv2d(x, wt, stride=stride)
+    y.backward(dz)
+    dw = ops.conv2d_wgrad(to_padded_nhwc(x.detach()), to_padded_nhwc(dz), h, w, k, stride)
+    assert (dw - wt.grad).abs().max().item() <= 1e-3 * wt.grad.abs().max().item()      # fp32 accumulate / output
+    wf = wt.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k, cout).contiguous().to(torch.bfloat16)
+    dzn = to_padded_nhwc(dz)
+    if stride != (1, 1):
+        dzn = ops.zero_upsample(dzn, ho, wo, stride)
+    dx = ops.nhwc_to_nchw(ops.conv2d_fprop(dzn, wf, h, w, k, (1, 1), ops.ACT_NONE), h, w)
+    assert (dx - x.grad).abs().max().item() <= 8e-3 * x.grad.abs().max().item()        # bf16 output
+
+
+def test_encoder_training_path_gradients(cuda_lib):
+    """Full trunk forward + backward on tcgen05 (autograd Function) against torch fp32 autograd."""
+    from delora_b200 import synthetic
+    from delora_b200.models.model import OdometryModel
+    from delora_b200.models.tc_encoder import TensorCoreEncoder
+    h, w, b = 64, 512, 2
+    cfg = synthetic.fov_config(h=h, w=w, device=DEV)
+    cfg.update({"pre_feature_extraction": False, "resnet_outputs": 1000, "use_dropout": False, "layers": [2, 2, 2, 2],
+                "factor_fewer_resnet_channels": 1, "activation_fct": "tanh", "use_single_mlp_at_output": False})
+    torch.manual_seed(0)
+    model = OdometryModel(cfg).to(DEV)
+    enc = TensorCoreEncoder(model)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    img1 = torch.randn(b, 4, h, w, device=DEV, generator=g) * 5.0
+    img2 = torch.randn(b, 4, h, w, device=DEV, generator=g) * 5.0
+    sel = torch.randn(b, 512, device=DEV, generator=g)
+    model.zero_grad()
+    (model.forward_features(image_1=img1, image_2=img2)[3].mean(dim=(2, 3)) * sel).sum().backward()
+    ref = [p.grad.clone() for p in enc.trunk_parameters()]
+    model.zero_grad()
+    pooled = enc.pooled_features(img1, img2)
+    (pooled * sel).sum().backward()
+    cosines = [F.cosine_similarity(p.grad.flatten(), r.flatten(), dim=0).item()
+               for p, r in zip(enc.trunk_parameters(), ref)]
+    assert len(cosines) == 20 and min(cosines[1:]) > 0.999 and cosines[0] > 0.98, cosines
+    # model-level: training forward with the flag goes through the differentiable tcgen05 trunk
+    model.config["use_tensor_core_encoder"] = True
+    model.zero_grad()
+    t, q = model(image_1=img1, image_2=img2)
+    (t.sum() + q.sum()).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
