@@ -272,6 +272,44 @@ def run_ours(args):
     d2h_bytes = sum(t.numel() * t.element_size() for t in out_host[0])
     assert abs(out_host[0][0][0, 1].item() - losses0[1]) <= 1e-6 * abs(losses0[1]) + 1e-12
 
+    # ---------------- full training step (BASELINE configs[2]/[3] shape), informational ----------------
+    train = None
+    if args.train_steps > 0:
+        try:
+            from delora_b200.train_step import SyntheticTrainStep
+            tcfg = synthetic.fov_config(h=H, w=W, device=device)
+            tb = args.train_batch
+            tpts = torch.zeros((2 * tb, 3, n_max), dtype=torch.float32)
+            tcnt = torch.zeros((2 * tb,), dtype=torch.int32)
+            for i in range(tb):
+                s1, s2, _, _ = raw[i % len(raw)]
+                tpts[i, :, :s1.shape[1]] = s1
+                tpts[tb + i, :, :s2.shape[1]] = s2
+                tcnt[i], tcnt[tb + i] = s1.shape[1], s2.shape[1]
+            torch.manual_seed(1234)
+            ts = SyntheticTrainStep(tcfg, tb, n_max, use_tensor_cores=True)
+            ts.load(tpts.to(device), tcnt.to(device))
+            for _ in range(3):
+                ts.step()
+            torch.cuda.synchronize()
+            barrier(world)
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for _ in range(args.train_steps):
+                tloss, _ = ts.step()
+            t1e.record()
+            torch.cuda.synchronize()
+            barrier(world)
+            tms = max_over_ranks(t0e.elapsed_time(t1e), world, device) / args.train_steps
+            train = {"workload": f"full training step, batch {tb}/GPU, 64x{W}: projection + normals + tcgen05 encoder "
+                                 "fwd/bwd (bf16) + heads + fused ICP loss fwd/bwd (fp32) + Adam"
+                                 + (" + flat NCCL gradient all-reduce (11.88 M fp32)" if world > 1 else ""),
+                     "ms_per_step": tms, "pairs_per_s": world * tb / (tms * 1e-3), "loss": float(tloss),
+                     "encoder_gflop_per_step": 3 * 96.17 * tb}
+            del ts
+        except Exception as e:                      # informational leg: never takes the headline down
+            train = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -329,6 +367,7 @@ def run_ours(args):
                          "sample": f"{cpu_n} pairs at 64x2048 through oracle.pair_forward_backward "
                                    f"(torch {torch.__version__} CPU + scipy cKDTree), {cores} of {os.cpu_count()} host threads "
                                    f"(best of a sweep), {cpu_dt:.1f} s"},
+        "train_step": train,
         "clocks": clocks, "wall_s_timed_region": t_wall,
         "check": {"loss_po2pl": losses0[1], "loss_pl2pl": losses0[2], "pairs": losses0[3],
                   "cpu_loss_po2pl": out["loss_po2pl"], "cpu_loss_pl2pl": out["loss_pl2pl"]},
@@ -345,6 +384,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-pairs", type=int, default=3, help="pairs timed for the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--train-steps", type=int, default=5, help="steps of the informational full-training-step leg (0 = skip)")
+    ap.add_argument("--train-batch", type=int, default=16)
     ap.add_argument("--rotate", type=int, default=ROTATE, help="rotating input sets (1 only for profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

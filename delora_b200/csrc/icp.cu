@@ -308,7 +308,10 @@ using namespace delora;
 extern "C" int delora_icp_partial_rows(int src_stride) { return (src_stride + 31) / 32; }
 
 extern "C" int64_t delora_icp_scratch_floats(int B, int src_stride) {
-    return (int64_t)B * delora_icp_partial_rows(src_stride) * DELORA_ICP_PARTIAL + (int64_t)B * DELORA_ICP_PARTIAL + B;
+    // partial rows + column sums + counters (+ the dense kernel's 4x16-cell range pyramid: 2 floats per block,
+    // at most src_stride/64 + H + W/16 + 1 <= src_stride/16 + 64 blocks per pair)
+    return (int64_t)B * delora_icp_partial_rows(src_stride) * DELORA_ICP_PARTIAL + (int64_t)B * DELORA_ICP_PARTIAL + B + 2 +
+           (int64_t)B * 2 * (src_stride / 16 + 4096);
 }
 
 extern "C" int delora_icp_fwd_bwd(const delora_f4* src_pts4, const delora_f4* src_nrm4, const int32_t* n_src,

@@ -13,6 +13,7 @@
 // failing lane needs.  Control flow is warp-uniform (no divergence), adjacent lanes read adjacent
 // cells (coalesced, L1-resident), and the guard is the same proof as in icp.cu: all unsearched
 // targets lie beyond a border half-plane (azimuth) or cone (elevation) of the lane's window.
+#include <stdlib.h>
 #include "icp_common.cuh"
 
 namespace delora {
@@ -80,12 +81,62 @@ __device__ __noinline__ int nn_exact_rescan(const float4* __restrict__ tg, int H
     return bj;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Range pyramid for the far / misaligned case.  The strip search above certifies exactness with a
+// purely ANGULAR bound, so a source point that is d away from the target surface has to scan every
+// cell within the angle asin(d/r) -- thousands of cells when the predicted transform is still poor
+// (d ~ 1 m), although almost all of them are provably farther than d once their RANGE is taken into
+// account.  Blocks of 4 x 16 cells carry [min, max] of |t|; a block whose lower bound
+//     min over rho in [rmin, rmax] of (r_s - rho)^2 + 4 r_s rho sin^2(theta/2),
+//     sin^2(theta/2) >= max( sin^2(gap_el/2), cos(e_s) * min cos(e_blk) * sin^2(gap_az/2) )
+// exceeds the current best distance cannot hold the nearest neighbour and is skipped.
+constexpr int kBlkH = 4, kBlkW = 16;
+__device__ unsigned int g_dbg[8];     // phase-2 statistics (owners, blocks tested, blocks scanned, max scanned/owner, warps)
+constexpr int kDefaultMaxStrips = 64; // strip expansions before a lane switches to the block search (measured:
+                                      // 24 -> +25 % on well-aligned pairs from serialised owners, 64 -> +2 %)
+
+__global__ void __launch_bounds__(256)
+block_range_kernel(const float4* __restrict__ grid, int H, int W, int nbh, int nbw, float2* __restrict__ blk) {
+    const int b = blockIdx.y;
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nbh * nbw) return;
+    const int br = warp / nbw, bc = warp % nbw;
+    float lo = 3.0e38f, hi = -1.0f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        const int row = br * kBlkH + (c >> 4), col = bc * kBlkW + (c & 15);
+        if (row < H && col < W) {
+            const float4 t = __ldg(grid + (size_t)b * H * W + (size_t)row * W + col);
+            if (__float_as_int(t.w) >= 0) {
+                const float rr = sqrtf(fmaf(t.z, t.z, fmaf(t.y, t.y, t.x * t.x)));
+                lo = fminf(lo, rr); hi = fmaxf(hi, rr);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    // widen by a relative 1e-6 so that the bound stays conservative against the fp32 norm rounding
+    if (lane == 0) blk[(size_t)b * nbh * nbw + warp] = make_float2(lo * (1.0f - 1e-6f), hi * (1.0f + 1e-6f));
+}
+
+__device__ __forceinline__ void nn2_merge(NN2& a, float bm1, float bm2, int bj) {
+    if (bj >= 0 && bj == a.j1) { a.m2 = fminf(a.m2, bm2); return; }     // the same cell seen twice is not a tie
+    const bool take = (bm1 < a.m1) || (bm1 == a.m1 && bj >= 0 && (a.j1 < 0 || bj < a.j1));
+    const float lose = take ? a.m1 : bm1;                   // the larger of the two minima
+    a.m2 = fminf(fminf(a.m2, bm2), (bj >= 0 && a.j1 >= 0) ? lose : 3.0e38f);
+    if (take) { a.m1 = bm1; a.j1 = bj; }
+}
+
 template <bool PO2PO>
 __global__ void __launch_bounds__(kDenseThreads, 8)
 icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__ src_ngrid,
                  const float* __restrict__ T, const float4* __restrict__ tgt_grid,
-                 const float4* __restrict__ tgt_ngrid, GridParams g, uint32_t flags,
-                 float* __restrict__ partial_rows, int rows_per_pair) {
+                 const float4* __restrict__ tgt_ngrid, const float2* __restrict__ blk_range, int nbh, int nbw,
+                 int max_strips, GridParams g, uint32_t flags, float* __restrict__ partial_rows, int rows_per_pair) {
     const int b = blockIdx.y;
     const int H = g.H, W = g.W, HW = H * W;
     const float4* __restrict__ tg = tgt_grid + (size_t)b * HW;
@@ -126,6 +177,8 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
         // warp-uniform window extents around every lane's own (rc, cc); the 3 x 5 start window is
         // fully unrolled: 15 independent loads in flight
         int e_dn = 1, e_up = 1, e_lf = 2, e_rt = 2;
+        bool ext_private = false;      // set for lanes whose extents were widened by the block search
+        (void)ext_private;
         if (H >= 3 && W >= 5) {
             int col[5];
 #pragma unroll
@@ -146,12 +199,14 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
         float b_up = (rc + e_up < H - 1) ? border_bound(f_up + (float)e_up, g.dv_rad, r) : kInf;
         float b_lf = (e_lf + e_rt + 1 >= W) ? kInf : border_bound(f_lf + (float)e_lf, g.du_rad, rxy);
         float b_rt = (e_lf + e_rt + 1 >= W) ? kInf : border_bound(f_rt + (float)e_rt, g.du_rad, rxy);
-        while (true) {
+        unsigned pending = 0u;                                   // lanes that still fail after kMaxStrips strips
+        for (int strip = 0;; ++strip) {
             const float bmin = fminf(fminf(b_dn, b_up), fminf(b_lf, b_rt));
             const bool done = !active || bmin >= kInf ||
                               (nn.j1 >= 0 && sqrtf(nn.m1) * 1.00001f <= bmin * 0.9995f);
             const unsigned failing = __ballot_sync(0xffffffffu, !done);
             if (failing == 0u) break;
+            if (strip >= max_strips) { pending = failing; break; }
             const int my_side = (bmin == b_dn) ? 0 : (bmin == b_up) ? 1 : (bmin == b_lf) ? 2 : 3;
             const int side = __shfl_sync(0xffffffffu, my_side, __ffs(failing) - 1);
             if (side < 2) {
@@ -188,6 +243,107 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
                 b_rt = full_w ? kInf : border_bound(f_rt + (float)e_rt, g.du_rad, rxy);
             }
         }
+        // ---------------- phase 2: warp-cooperative, range-pruned block search for the remaining lanes
+        const float2* __restrict__ blk = blk_range + (size_t)b * nbh * nbw;
+        const int lane = threadIdx.x & 31;
+        if (pending && (threadIdx.x & 31) == 0) { atomicAdd(&g_dbg[5], 1u); atomicMax(&g_dbg[6], (unsigned)__popc(pending)); }
+        while (pending) {
+            const int owner = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const float osx = __shfl_sync(0xffffffffu, sx, owner), osy = __shfl_sync(0xffffffffu, sy, owner),
+                        osz = __shfl_sync(0xffffffffu, sz, owner);
+            const float ous = __shfl_sync(0xffffffffu, us, owner), ovs = __shfl_sync(0xffffffffu, vs, owner);
+            const float orr = __shfl_sync(0xffffffffu, r, owner), orxy = __shfl_sync(0xffffffffu, rxy, owner);
+            const int orc = __shfl_sync(0xffffffffu, rc, owner), occ = __shfl_sync(0xffffffffu, cc, owner);
+            float obest = __shfl_sync(0xffffffffu, nn.m1, owner);         // running best d^2 (fp32), warp-uniform
+            const int obr = orc / kBlkH, obc = occ / kBlkW;
+            const float cos_es = orr > 0.0f ? orxy / orr : 1.0f;
+            NN2 loc;
+            loc.m1 = kInf; loc.m2 = kInf; loc.j1 = -1;
+            // Block rectangle that certifies the CURRENT best: grow it (warp-uniform scalar loops) until all
+            // four borders are at least d0 away; the best can only shrink while the rectangle is scanned, so
+            // one pass over its blocks is enough (no ring-by-ring dependency chain).
+            const float d0 = (obest < kInf) ? sqrtf(obest) * (1.00001f / 0.9995f) : kInf;
+            int br_lo = obr, br_hi = obr, bc_lo = obc, bc_hi = obc;            // bc_* unwrapped
+            while (br_lo > 0 && border_bound(ovs - ((float)(br_lo * kBlkH) - 0.5f) - kSlack, g.dv_rad, orr) < d0) --br_lo;
+            while (br_hi < nbh - 1 &&
+                   border_bound(((float)min(br_hi * kBlkH + kBlkH - 1, H - 1) + 0.5f) - ovs - kSlack, g.dv_rad, orr) < d0)
+                ++br_hi;
+            while (bc_hi - bc_lo + 1 < nbw &&
+                   border_bound(ous - ((float)(bc_lo * kBlkW) - 0.5f) - kSlack, g.du_rad, orxy) < d0) --bc_lo;
+            while (bc_hi - bc_lo + 1 < nbw &&
+                   border_bound(((float)(bc_hi * kBlkW + kBlkW - 1) + 0.5f) - ous - kSlack, g.du_rad, orxy) < d0) ++bc_hi;
+            const int nbc = bc_hi - bc_lo + 1, nblk = (br_hi - br_lo + 1) * nbc;
+            int dbg_scanned = 0;
+            for (int base = 0; base < nblk; base += 32) {
+                const int idx = base + lane;
+                const bool in = idx < nblk;
+                const int br = br_lo + (in ? idx / nbc : 0);
+                int bc = bc_lo + (in ? idx % nbc : 0), shift = 0;
+                if (bc < 0) { bc += nbw; shift = -W; } else if (bc >= nbw) { bc -= nbw; shift = W; }
+                bool ok = in;
+                float lb2 = kInf;
+                if (ok) {
+                    const float2 rg = __ldg(blk + br * nbw + bc);
+                    if (rg.y >= 0.0f) {
+                        const float v_lo = (float)(br * kBlkH) - 0.5f, v_hi = (float)min(br * kBlkH + kBlkH - 1, H - 1) + 0.5f;
+                        const float u_lo = (float)(bc * kBlkW + shift) - 0.5f,
+                                    u_hi = (float)(min(bc * kBlkW + kBlkW - 1, W - 1) + shift) + 0.5f;
+                        const float gv = fmaxf(fmaxf(v_lo - ovs, ovs - v_hi) - kSlack, 0.0f) * g.dv_rad;
+                        const float gu = fmaxf(fmaxf(u_lo - ous, ous - u_hi) - kSlack, 0.0f) * g.du_rad;
+                        const float sv = __sinf(fminf(0.5f * gv, kHalfPiF)), su = __sinf(fminf(0.5f * gu, kHalfPiF));
+                        const float e_lo = g.vf0 + v_lo * g.dv_rad, e_hi = g.vf0 + v_hi * g.dv_rad;
+                        const float c_blk = fmaxf(fminf(__cosf(e_lo), __cosf(e_hi)), 0.0f);
+                        const float S = fmaxf(sv * sv, cos_es * c_blk * su * su);
+                        const float rho = fminf(fmaxf(orr * (1.0f - 2.0f * S), rg.x), rg.y);
+                        const float dr_ = orr - rho;
+                        lb2 = fmaf(dr_, dr_, 4.0f * orr * rho * S) * 0.999f;
+                    } else {
+                        ok = false;                                       // empty block
+                    }
+                }
+                unsigned need = __ballot_sync(0xffffffffu, ok && lb2 <= obest * 1.001f);
+                dbg_scanned += __popc(need);
+                while (need) {
+                    const int sel = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int sbr = __shfl_sync(0xffffffffu, br, sel), sbc = __shfl_sync(0xffffffffu, bc, sel);
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int c = lane + 32 * h2;
+                        const int row = sbr * kBlkH + (c >> 4), col = sbc * kBlkW + (c & 15);
+                        const bool cok = row < H && col < W;
+                        const int j = min(row, H - 1) * W + min(col, W - 1);
+                        nn2_eval(__ldg(tg + j), j, osx, osy, osz, loc, cok);
+                    }
+                }
+                // tighten the running best with what this chunk found (prunes the following chunks harder)
+                float wm = loc.m1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) wm = fminf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+                obest = fminf(obest, wm);
+            }
+            if (lane == 0) {
+                atomicAdd(&g_dbg[0], 1u); atomicAdd(&g_dbg[1], (unsigned)nblk); atomicAdd(&g_dbg[2], (unsigned)dbg_scanned);
+                atomicMax(&g_dbg[3], (unsigned)dbg_scanned); atomicMax(&g_dbg[4], (unsigned)nblk);
+            }
+            // merge the 32 partial results, then into the owner's own phase-1 result
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float bm1 = __shfl_xor_sync(0xffffffffu, loc.m1, o), bm2 = __shfl_xor_sync(0xffffffffu, loc.m2, o);
+                const int bj = __shfl_xor_sync(0xffffffffu, loc.j1, o);
+                nn2_merge(loc, bm1, bm2, bj);
+            }
+            if (lane == owner) {
+                nn2_merge(nn, loc.m1, loc.m2, loc.j1);
+                // extents of everything that has been examined (for the float64 tie re-ranking)
+                e_dn = max(e_dn, rc - br_lo * kBlkH);
+                e_up = max(e_up, min(br_hi * kBlkH + kBlkH - 1, H - 1) - rc);
+                e_lf = max(e_lf, min(cc - bc_lo * kBlkW, W - 1));
+                e_rt = max(e_rt, min(bc_hi * kBlkW + kBlkW - 1 - cc, W - 1));
+                ext_private = true;
+            }
+        }
         best_j = nn.j1;
         if (active && best_j >= 0 && nn.m2 <= nn.m1 * (1.0f + kNNBand))
             best_j = nn_exact_rescan(tg, H, W, rc, cc, e_dn, e_up, e_lf, e_rt, sx, sy, sz, nn.m1 * (1.0f + kNNBand));
@@ -209,6 +365,12 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
 
 using namespace delora;
 
+extern "C" int delora_debug_counters(unsigned int* out8, int reset) {
+    if (out8) cudaMemcpyFromSymbol(out8, delora::g_dbg, 8 * sizeof(unsigned int));
+    if (reset) { unsigned int z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(delora::g_dbg, z, sizeof(z)); }
+    return 0;
+}
+
 extern "C" int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_f4* src_ngrid, const float* T,
                                         const delora_f4* tgt_grid, const delora_f4* tgt_ngrid, int B, int H, int W,
                                         double hfov0, double hfov1, double vfov0, double vfov1, float lambda_po2pl,
@@ -222,14 +384,25 @@ extern "C" int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_
     const IcpScratch sc = icp_scratch(scratch, B, rows);
     dim3 grid((HW + kDenseThreads - 1) / kDenseThreads, B);
     cudaStream_t st = (cudaStream_t)stream;
+    int max_strips = kDefaultMaxStrips;
+    if (const char* e = getenv("DELORA_ICP_MAX_STRIPS")) max_strips = atoi(e);      // tuning knob (tests / profiling)
+    // range pyramid of the TARGET grids, kept behind the partial rows / column sums / counters of the scratch
+    const int nbh = (H + kBlkH - 1) / kBlkH, nbw = (W + kBlkW - 1) / kBlkW;
+    float2* blk = reinterpret_cast<float2*>(scratch + (size_t)B * delora_icp_partial_rows(HW) * DELORA_ICP_PARTIAL +
+                                            (size_t)B * DELORA_ICP_PARTIAL + (((size_t)B + 1) & ~(size_t)1));
+    {
+        dim3 gb((nbh * nbw * 32 + 255) / 256, B);
+        block_range_kernel<<<gb, 256, 0, st>>>((const float4*)tgt_grid, H, W, nbh, nbw, blk);
+        DELORA_CHECK_LAUNCH("block_range_kernel");
+    }
     if (flags & DELORA_LOSS_PO2PO) {
         icp_dense_kernel<true><<<grid, kDenseThreads, 0, st>>>((const float4*)src_grid, (const float4*)src_ngrid, T,
-                                                               (const float4*)tgt_grid, (const float4*)tgt_ngrid, g,
-                                                               flags, sc.rows, rows);
+                                                               (const float4*)tgt_grid, (const float4*)tgt_ngrid, blk,
+                                                               nbh, nbw, max_strips, g, flags, sc.rows, rows);
     } else {
         icp_dense_kernel<false><<<grid, kDenseThreads, 0, st>>>((const float4*)src_grid, (const float4*)src_ngrid, T,
-                                                                (const float4*)tgt_grid, (const float4*)tgt_ngrid, g,
-                                                                flags, sc.rows, rows);
+                                                                (const float4*)tgt_grid, (const float4*)tgt_ngrid, blk,
+                                                                nbh, nbw, max_strips, g, flags, sc.rows, rows);
     }
     DELORA_CHECK_LAUNCH("icp_dense_kernel");
     return launch_icp_finalize(scratch, B, rows, lambda_po2pl, flags, losses, grad_T, st);

@@ -45,4 +45,21 @@ for fn, name in ((t_proj, "projection"), (t_norm, "normals"), (t_icp, "icp_dense
 step = timeit(lambda: pipe.step(), "full step")
 print(f"sum of parts {tot*1e3:.1f} us; step {step*1e3:.1f} us -> {B/(step*1e-3):.0f} pairs/s")
 print("losses", pipe.losses[0].tolist())
+import ctypes
+dbg = (ctypes.c_uint * 8)()
+L.delora_debug_counters(None, 1); t_icp(); torch.cuda.synchronize(); L.delora_debug_counters(dbg, 1)
+print("phase2 stats: owners %d, blocks tested %d, blocks scanned %d, max scanned/owner %d, max rect blocks %d, warps in phase2 %d, max owners/warp %d" % tuple(dbg[:7]))
+# misaligned case: identity transform instead of the (nearly correct) predicted one -> NN distances ~0.5 m
+import torch as _t
+pipe.transform.copy_(_t.eye(4, device="cuda")[:3, :].reshape(1, 12).repeat(B, 1))
+timeit(t_icp, "icp_identityT")
+print("losses(identity T)", pipe.losses[0].tolist())
+from delora_b200 import synthetic as _syn
+import math as _m
+tb = _t.from_numpy(_syn.transform_matrix(2.0, 1.0, 0.3, _m.radians(10.0), _m.radians(2.0), 0.0)).float().cuda()
+pipe.transform.copy_(tb[:3, :].reshape(1, 12).repeat(B, 1))
+timeit(t_icp, "icp_badT", iters=5)
+L.delora_debug_counters(None, 1); t_icp(); torch.cuda.synchronize(); L.delora_debug_counters(dbg, 1)
+print("badT phase2 stats: owners %d, blocks tested %d, blocks scanned %d, max scanned/owner %d, max rect blocks %d, warps in phase2 %d, max owners/warp %d" % tuple(dbg[:7]))
+print("losses(bad T)", pipe.losses[0].tolist())
 

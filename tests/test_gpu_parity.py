@@ -295,6 +295,42 @@ def test_dense_icp_matches_list_icp(name, golden, cuda_lib):
                                                           & (images[:, 2] != 0)).reshape(2, -1)).all())
 
 
+@pytest.mark.parametrize("name,dx,yaw_deg", [("kitti_64x720", 1.5, 4.0), ("small_16x180", 0.8, 10.0),
+                                             ("kitti_64x2048", 0.6, 1.5)])
+def test_dense_icp_large_misalignment(name, dx, yaw_deg, golden, cuda_lib):
+    """A poor transform (untrained network): NN distances of ~1 m force the range-pruned block search.
+    The dense kernel must still return the exact NN statistics: same pair count and sums as the CSR kernel
+    (independent search code) and as the oracle (cKDTree)."""
+    from delora_b200 import ops, synthetic
+    meta, cfg, _, _, _, out = oracle_case(name, golden)
+    h, w = meta["H"], meta["W"]
+    hf, vf = fov(cfg)
+    t_bad = synthetic.transform_matrix(dx, -0.3, 0.1, math.radians(yaw_deg), math.radians(1.0), 0.0)
+    t_bad = torch.from_numpy(t_bad).float()
+    images = torch.cat((out["image_1"], out["image_2"])).to(DEV)
+    nrm_img, pg, ng = ops.normals(images, grids=True)
+    T = t_bad[:3, :].reshape(1, 12).contiguous().to(DEV)
+    losses, grad_t = ops.icp_dense_fwd_bwd(pg[1:2].contiguous(), ng[1:2].contiguous(), T, pg[0:1].contiguous(),
+                                           ng[0:1].contiguous(), h, w, hf, vf)
+    pts4, nrm4, cs, counts = ops.lists_from_images(images, nrm_img)
+    l2, g2, _, _, _ = ops.icp_fwd_bwd(pts4[1:2].contiguous(), nrm4[1:2].contiguous(), counts[1:2].contiguous(), T,
+                                      pts4[0:1].contiguous(), nrm4[0:1].contiguous(), cs[0:1].contiguous(), h, w,
+                                      hf, vf)
+    assert float(l2[0, 3]) == float(losses[0, 3])
+    assert torch.allclose(l2[0, :3].cpu(), losses[0, :3].cpu(), rtol=2e-6, atol=0)
+    assert torch.allclose(g2.cpu(), grad_t.cpu(), rtol=1e-4, atol=1e-7)
+    if name != "kitti_64x2048":          # oracle (cKDTree) cross-check on the smaller cases
+        tm = t_bad.view(1, 4, 4)
+        # same normals as the kernel so that only the search differs
+        p1, n1 = pts4[0, :int(counts[0]), :3].cpu(), nrm4[0, :int(counts[0]), :3].cpu()
+        p2, n2 = pts4[1, :int(counts[1]), :3].cpu(), nrm4[1, :int(counts[1]), :3].cpu()
+        lo, aux = orc.icp_losses(orc.transform_point_cloud(tm, p2.t()[None]), orc.rotate_point_cloud(tm, n2.t()[None]),
+                                 p1.t()[None].contiguous(), n1.t()[None].contiguous(), return_aux=True)
+        assert aux["num_pairs"] == int(losses[0, 3])
+        assert float(losses[0, 1]) == pytest.approx(float(lo["loss_po2pl"]), rel=1e-5)
+        assert float(losses[0, 2]) == pytest.approx(float(lo["loss_pl2pl"]), rel=1e-5)
+
+
 def test_generic_lists_shuffled_and_po2po(golden, cuda_lib):
     """Arbitrary (shuffled, with out-of-FOV points) lists through delora_grid_build; po2po on."""
     from delora_b200 import ops
