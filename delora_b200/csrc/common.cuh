@@ -36,6 +36,12 @@ struct GridParams {
     float hf0, hspan, hinv, wm1;   // u = (atan2(y,x) - hf0) / hspan * wm1
     float vf0, vspan, vinv, hm1;   // v = (atan2(z,|xy|) - vf0) / vspan * hm1
     float du_rad, dv_rad;          // radians per pixel step (hspan/wm1, vspan/hm1)
+    // The column index continues across the +-180 deg seam as if column W followed column W-1 at one pixel
+    // pitch, but the real gap between the centres of columns W-1 and 0 is 2 pi - hspan.  When a pixel is
+    // WIDER than that gap (W = 720: 0.50 deg vs 0.2 deg) an "unwrapped" pixel distance across the seam
+    // overstates the angle by seam_px pixels; every exactness bound that looks across the seam subtracts it.
+    float seam_px;                 // max(0, 1 - (2 pi - hspan) / du_rad)
+    float circ_px;                 // 2 pi / du_rad: pixels once around
     int div_mode;
 };
 
@@ -46,6 +52,8 @@ inline GridParams make_grid(int H, int W, double hf0, double hf1, double vf0, do
     g.vf0 = (float)vf0; g.vspan = (float)(vf1 - vf0); g.vinv = 1.0f / g.vspan; g.hm1 = (float)(H - 1);
     g.du_rad = (W > 1) ? (float)((hf1 - hf0) / (double)(W - 1)) : 1.0f;
     g.dv_rad = (H > 1) ? (float)((vf1 - vf0) / (double)(H - 1)) : 1.0f;
+    g.seam_px = fmaxf(0.0f, 1.0f - (float)((6.283185307179586 - (hf1 - hf0)) / (double)g.du_rad));
+    g.circ_px = (float)(6.283185307179586 / (double)g.du_rad);
     g.div_mode = div_mode;
     return g;
 }

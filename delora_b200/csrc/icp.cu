@@ -77,8 +77,9 @@ __device__ __forceinline__ NNBest nn_search(const GridParams& g, const float4* _
         }
         const int width = c_hi - c_lo + 1;
         if (width < W) {
-            const float dl = (us - ((float)c_lo - 0.5f) - 2e-3f) * g.du_rad;
-            const float dr = (((float)c_hi + 0.5f) - us - 2e-3f) * g.du_rad;
+            // a border at or beyond the seam: see GridParams::seam_px
+            const float dl = (us - ((float)c_lo - 0.5f) - 2e-3f - (c_lo <= 0 ? g.seam_px : 0.0f)) * g.du_rad;
+            const float dr = (((float)c_hi + 0.5f) - us - 2e-3f - (c_hi >= W - 1 ? g.seam_px : 0.0f)) * g.du_rad;
             b_lf = dl <= 0.0f ? 0.0f : rxy * __sinf(fminf(dl, kHalfPiF));
             b_rt = dr <= 0.0f ? 0.0f : rxy * __sinf(fminf(dr, kHalfPiF));
         }

@@ -123,6 +123,16 @@ block_range_kernel(const float4* __restrict__ grid, int H, int W, int nbh, int n
     if (lane == 0) blk[(size_t)b * nbh * nbw + warp] = make_float2(lo * (1.0f - 1e-6f), hi * (1.0f + 1e-6f));
 }
 
+// first / last pixel column of the (unwrapped) block column bc; bc in [-nbw, 2 nbw)
+__device__ __forceinline__ int blk_u_lo(int bc, int nbw, int W) {
+    const int k = (bc < 0) ? -1 : (bc >= nbw) ? 1 : 0;
+    return (bc - k * nbw) * kBlkW + k * W;
+}
+__device__ __forceinline__ int blk_u_hi(int bc, int nbw, int W) {
+    const int k = (bc < 0) ? -1 : (bc >= nbw) ? 1 : 0;
+    return min((bc - k * nbw) * kBlkW + kBlkW - 1, W - 1) + k * W;
+}
+
 __device__ __forceinline__ void nn2_merge(NN2& a, float bm1, float bm2, int bj) {
     if (bj >= 0 && bj == a.j1) { a.m2 = fminf(a.m2, bm2); return; }     // the same cell seen twice is not a tie
     const bool take = (bm1 < a.m1) || (bm1 == a.m1 && bj >= 0 && (a.j1 < 0 || bj < a.j1));
@@ -197,8 +207,11 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
         }
         float b_dn = (rc - e_dn > 0) ? border_bound(f_dn + (float)e_dn, g.dv_rad, r) : kInf;
         float b_up = (rc + e_up < H - 1) ? border_bound(f_up + (float)e_up, g.dv_rad, r) : kInf;
-        float b_lf = (e_lf + e_rt + 1 >= W) ? kInf : border_bound(f_lf + (float)e_lf, g.du_rad, rxy);
-        float b_rt = (e_lf + e_rt + 1 >= W) ? kInf : border_bound(f_rt + (float)e_rt, g.du_rad, rxy);
+        // a border at or beyond the +-180 deg seam is seam_px closer than its unwrapped pixel distance
+        float b_lf = (e_lf + e_rt + 1 >= W) ? kInf
+                   : border_bound(f_lf + (float)e_lf - (cc - e_lf <= 0 ? g.seam_px : 0.0f), g.du_rad, rxy);
+        float b_rt = (e_lf + e_rt + 1 >= W) ? kInf
+                   : border_bound(f_rt + (float)e_rt - (cc + e_rt >= W - 1 ? g.seam_px : 0.0f), g.du_rad, rxy);
         unsigned pending = 0u;                                   // lanes that still fail after kMaxStrips strips
         for (int strip = 0;; ++strip) {
             const float bmin = fminf(fminf(b_dn, b_up), fminf(b_lf, b_rt));
@@ -239,8 +252,8 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
                 }
                 if (side == 2) e_lf += step; else e_rt += step;
                 const bool full_w = (e_lf + e_rt + 1 >= W);
-                b_lf = full_w ? kInf : border_bound(f_lf + (float)e_lf, g.du_rad, rxy);
-                b_rt = full_w ? kInf : border_bound(f_rt + (float)e_rt, g.du_rad, rxy);
+                b_lf = full_w ? kInf : border_bound(f_lf + (float)e_lf - (cc - e_lf <= 0 ? g.seam_px : 0.0f), g.du_rad, rxy);
+                b_rt = full_w ? kInf : border_bound(f_rt + (float)e_rt - (cc + e_rt >= W - 1 ? g.seam_px : 0.0f), g.du_rad, rxy);
             }
         }
         // ---------------- phase 2: warp-cooperative, range-pruned block search for the remaining lanes
@@ -269,28 +282,35 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
             while (br_hi < nbh - 1 &&
                    border_bound(((float)min(br_hi * kBlkH + kBlkH - 1, H - 1) + 0.5f) - ovs - kSlack, g.dv_rad, orr) < d0)
                 ++br_hi;
+            // (unwrapped block columns: W need not be a multiple of kBlkW, so the pixel span of block column
+            //  bc outside [0, nbw) is that of its wrapped twin shifted by +-W, not bc * kBlkW)
             while (bc_hi - bc_lo + 1 < nbw &&
-                   border_bound(ous - ((float)(bc_lo * kBlkW) - 0.5f) - kSlack, g.du_rad, orxy) < d0) --bc_lo;
+                   border_bound(ous - ((float)blk_u_lo(bc_lo, nbw, W) - 0.5f) - kSlack - (bc_lo <= 0 ? g.seam_px : 0.0f),
+                                g.du_rad, orxy) < d0) --bc_lo;
             while (bc_hi - bc_lo + 1 < nbw &&
-                   border_bound(((float)(bc_hi * kBlkW + kBlkW - 1) + 0.5f) - ous - kSlack, g.du_rad, orxy) < d0) ++bc_hi;
+                   border_bound(((float)blk_u_hi(bc_hi, nbw, W) + 0.5f) - ous - kSlack - (bc_hi >= nbw - 1 ? g.seam_px : 0.0f),
+                                g.du_rad, orxy) < d0) ++bc_hi;
             const int nbc = bc_hi - bc_lo + 1, nblk = (br_hi - br_lo + 1) * nbc;
             int dbg_scanned = 0;
             for (int base = 0; base < nblk; base += 32) {
                 const int idx = base + lane;
                 const bool in = idx < nblk;
                 const int br = br_lo + (in ? idx / nbc : 0);
-                int bc = bc_lo + (in ? idx % nbc : 0), shift = 0;
-                if (bc < 0) { bc += nbw; shift = -W; } else if (bc >= nbw) { bc -= nbw; shift = W; }
+                int bc = bc_lo + (in ? idx % nbc : 0);
+                bc += (bc < 0) ? nbw : 0;
+                bc -= (bc >= nbw) ? nbw : 0;
                 bool ok = in;
                 float lb2 = kInf;
                 if (ok) {
                     const float2 rg = __ldg(blk + br * nbw + bc);
                     if (rg.y >= 0.0f) {
                         const float v_lo = (float)(br * kBlkH) - 0.5f, v_hi = (float)min(br * kBlkH + kBlkH - 1, H - 1) + 0.5f;
-                        const float u_lo = (float)(bc * kBlkW + shift) - 0.5f,
-                                    u_hi = (float)(min(bc * kBlkW + kBlkW - 1, W - 1) + shift) + 0.5f;
+                        const float u_lo = (float)(bc * kBlkW) - 0.5f, u_hi = (float)min(bc * kBlkW + kBlkW - 1, W - 1) + 0.5f;
                         const float gv = fmaxf(fmaxf(v_lo - ovs, ovs - v_hi) - kSlack, 0.0f) * g.dv_rad;
-                        const float gu = fmaxf(fmaxf(u_lo - ous, ous - u_hi) - kSlack, 0.0f) * g.du_rad;
+                        // azimuth gap ON THE CIRCLE: the direct way, or the other way round through the seam
+                        const float d1 = u_lo - ous, d2 = ous - u_hi;
+                        const float gpx = fminf(fmaxf(fmaxf(d1, d2), 0.0f), g.circ_px + fminf(d1, d2));
+                        const float gu = fmaxf(gpx - kSlack, 0.0f) * g.du_rad;
                         const float sv = __sinf(fminf(0.5f * gv, kHalfPiF)), su = __sinf(fminf(0.5f * gu, kHalfPiF));
                         const float e_lo = g.vf0 + v_lo * g.dv_rad, e_hi = g.vf0 + v_hi * g.dv_rad;
                         const float c_blk = fmaxf(fminf(__cosf(e_lo), __cosf(e_hi)), 0.0f);
@@ -339,8 +359,8 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
                 // extents of everything that has been examined (for the float64 tie re-ranking)
                 e_dn = max(e_dn, rc - br_lo * kBlkH);
                 e_up = max(e_up, min(br_hi * kBlkH + kBlkH - 1, H - 1) - rc);
-                e_lf = max(e_lf, min(cc - bc_lo * kBlkW, W - 1));
-                e_rt = max(e_rt, min(bc_hi * kBlkW + kBlkW - 1 - cc, W - 1));
+                e_lf = max(e_lf, min(cc - blk_u_lo(bc_lo, nbw, W), W - 1));
+                e_rt = max(e_rt, min(blk_u_hi(bc_hi, nbw, W) - cc, W - 1));
                 ext_private = true;
             }
         }

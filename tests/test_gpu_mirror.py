@@ -87,7 +87,7 @@ def test_icp_losses_module_forward_backward(po2po, normal_loss, golden, cuda_lib
     assert set(losses) == {"loss_po2po", "loss_po2pl", "loss_po2pl_pointwise", "loss_pl2pl"}
     (2.0 * losses["loss_po2pl"] + 0.5 * losses["loss_pl2pl"] + losses["loss_po2po"]).sum().backward()
     for k in ("loss_po2pl", "loss_pl2pl", "loss_po2po"):
-        assert float(losses[k]) == pytest.approx(float(lo[k]), rel=1e-5, abs=1e-12), k
+        assert float(losses[k].detach()) == pytest.approx(float(lo[k].detach()), rel=1e-5, abs=1e-12), k
     assert plotting["scan_2_transformed"].shape == (1, 3, aux["num_pairs"])
     assert torch.equal(plotting["scan_2_transformed"].detach().cpu(), aux["source_points_where_normals"].detach())
     assert losses["loss_po2pl_pointwise"].shape == (1, 3, aux["num_pairs"])
@@ -174,9 +174,9 @@ def test_deployer_step_matches_per_sample_reference_flow(tmp_path, cuda_lib):
         run["po2pl"] += float(lo["loss_po2pl"])
         run["pl2pl"] += float(lo["loss_pl2pl"])
         run["pc"] += run["po2pl"] + run["pl2pl"]                            # :309-312 (running sums!)
-    assert float(el["loss_po2pl_epoch"]) == pytest.approx(run["po2pl"] / 2, rel=2e-5)
-    assert float(el["loss_pl2pl_epoch"]) == pytest.approx(run["pl2pl"] / 2, rel=2e-5)
-    assert float(el["loss_point_cloud_epoch"]) == pytest.approx(run["pc"] / 2, rel=2e-5)
+    assert float(np.asarray(el["loss_po2pl_epoch"]).reshape(-1)[0]) == pytest.approx(run["po2pl"] / 2, rel=2e-5)
+    assert float(np.asarray(el["loss_pl2pl_epoch"]).reshape(-1)[0]) == pytest.approx(run["pl2pl"] / 2, rel=2e-5)
+    assert float(np.asarray(el["loss_point_cloud_epoch"]).reshape(-1)[0]) == pytest.approx(run["pc"] / 2, rel=2e-5)
 
 
 def test_trainer_runs_and_checkpoints(tmp_path, cuda_lib):

@@ -296,7 +296,11 @@ def test_dense_icp_matches_list_icp(name, golden, cuda_lib):
 
 
 @pytest.mark.parametrize("name,dx,yaw_deg", [("kitti_64x720", 1.5, 4.0), ("small_16x180", 0.8, 10.0),
-                                             ("kitti_64x2048", 0.6, 1.5)])
+                                             ("kitti_64x2048", 0.6, 1.5),
+                                             # re-projections that cross the +-180 deg seam; W = 180 is not a
+                                             # multiple of the 16-column range blocks (ragged last block column)
+                                             ("small_16x180", 0.5, 178.0), ("small_16x180", 2.0, -95.0),
+                                             ("kitti_64x720", 0.3, 181.0)])
 def test_dense_icp_large_misalignment(name, dx, yaw_deg, golden, cuda_lib):
     """A poor transform (untrained network): NN distances of ~1 m force the range-pruned block search.
     The dense kernel must still return the exact NN statistics: same pair count and sums as the CSR kernel
@@ -329,6 +333,41 @@ def test_dense_icp_large_misalignment(name, dx, yaw_deg, golden, cuda_lib):
         assert aux["num_pairs"] == int(losses[0, 3])
         assert float(losses[0, 1]) == pytest.approx(float(lo["loss_po2pl"]), rel=1e-5)
         assert float(losses[0, 2]) == pytest.approx(float(lo["loss_pl2pl"]), rel=1e-5)
+
+
+@pytest.mark.parametrize("name,n_transforms", [("small_16x180", 12), ("kitti_64x720", 4)])
+def test_dense_icp_arbitrary_transforms_vs_kdtree(name, n_transforms, golden, cuda_lib):
+    """Untrained-network regime: arbitrary rotations (any axis, up to 180 deg) and translations of metres.
+    Sources re-project anywhere (across the seam, outside the vertical FOV); the strip search gives up
+    and the range-pruned block search takes over.  Exactness is checked against cKDTree (oracle)."""
+    from delora_b200 import ops
+    meta, cfg, _, _, _, out = oracle_case(name, golden)
+    h, w = meta["H"], meta["W"]
+    hf, vf = fov(cfg)
+    images = torch.cat((out["image_1"], out["image_2"])).to(DEV)
+    nrm_img, pg, ng = ops.normals(images, grids=True)
+    pts4, nrm4, cs, counts = ops.lists_from_images(images, nrm_img)
+    p1, n1 = pts4[0, :int(counts[0]), :3].cpu(), nrm4[0, :int(counts[0]), :3].cpu()
+    p2, n2 = pts4[1, :int(counts[1]), :3].cpu(), nrm4[1, :int(counts[1]), :3].cpu()
+    gen = torch.Generator().manual_seed(77)
+    for k in range(n_transforms):
+        axis = torch.randn(3, generator=gen)
+        axis = axis / axis.norm()
+        ang = float(torch.rand(1, generator=gen)) * math.pi * (1.0 if k % 3 else 0.1)
+        kx = torch.tensor([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        rot = torch.eye(3) + math.sin(ang) * kx + (1 - math.cos(ang)) * (kx @ kx)
+        tm = torch.eye(4)
+        tm[:3, :3] = rot
+        tm[:3, 3] = (torch.rand(3, generator=gen) - 0.5) * torch.tensor([16.0, 16.0, 2.0]) * (1.0 if k % 2 else 0.1)
+        T = tm[:3, :].reshape(1, 12).contiguous().to(DEV)
+        losses, _ = ops.icp_dense_fwd_bwd(pg[1:2].contiguous(), ng[1:2].contiguous(), T, pg[0:1].contiguous(),
+                                          ng[0:1].contiguous(), h, w, hf, vf)
+        t4 = tm.view(1, 4, 4)
+        lo, aux = orc.icp_losses(orc.transform_point_cloud(t4, p2.t()[None]), orc.rotate_point_cloud(t4, n2.t()[None]),
+                                 p1.t()[None].contiguous(), n1.t()[None].contiguous(), return_aux=True)
+        assert aux["num_pairs"] == int(losses[0, 3]), (k, ang, tm[:3, 3])
+        assert float(losses[0, 1]) == pytest.approx(float(lo["loss_po2pl"]), rel=2e-5), (k, ang, tm[:3, 3])
+        assert float(losses[0, 2]) == pytest.approx(float(lo["loss_pl2pl"]), rel=2e-5), (k, ang, tm[:3, 3])
 
 
 def test_generic_lists_shuffled_and_po2po(golden, cuda_lib):

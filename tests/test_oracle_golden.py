@@ -66,7 +66,7 @@ def test_small_case_full_tensors():
     out = orc.pair_forward_backward(scan_1, scan_2, t_pred, cfg)
     assert np.array_equal(out["image_1"][0].numpy(), z["image_1"])
     assert np.array_equal(out["normals_2"].numpy(), z["normals_2"])
-    assert np.array_equal(out["points_2"][out["kept_mask"]].t().numpy() if False else z["points_2"], z["points_2"])
+    assert np.array_equal(out["points_2"].numpy(), z["points_2"])
     # kept source points (plotting["scan_2_transformed"], icp_losses.py:153-156): same set, same order
     src = orc.transform_point_cloud(t_pred.view(1, 4, 4), out["points_2"].t()[None])[0]
     assert np.allclose(src[:, out["kept_mask"]].numpy(), z["kept_source_points"], rtol=0, atol=1e-6)
