@@ -32,6 +32,7 @@ SIGNATURES = {
     "delora_pack_lists": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "delora_icp_partial_rows": (c_int, [c_int]),
     "delora_icp_scratch_floats": (c_i64, [c_int, c_int]),
+    "delora_icp_stats": (c_int, [c_void_p, c_int]),
     "delora_icp_dense_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                          c_double, c_double, c_double, c_double, c_float, c_u32, c_void_p,
                                          c_void_p, c_void_p, c_void_p]),
@@ -45,7 +46,8 @@ SIGNATURES = {
     "delora_conv2d_wgrad_scratch_floats": (c_i64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "delora_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_int, c_int, c_void_p]),
-    "delora_zero_upsample_nhwc_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "delora_zero_upsample_nhwc_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                               c_void_p]),
     "delora_images_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "delora_maxpool_w_nhwc_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "delora_maxpool_w_idx_nhwc_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -518,9 +518,9 @@ maxpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, in
 // flipped filter.  x [B,H+2,W+2,C] padded -> y [B,H*sh+2,W*sw+2,C] padded: y[h*sh, w*sw] = x[h, w], zeros
 // elsewhere (incl. correct circular halo columns and zero halo rows).
 __global__ void __launch_bounds__(256)
-zero_upsample_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int sh, int sw,
+zero_upsample_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int sh, int sw, int Ho, int Wo,
                      __nv_bfloat16* __restrict__ y) {
-    const int Ho = H * sh, Wo = W * sw, groups = C / 8;
+    const int groups = C / 8;
     const size_t total = (size_t)B * (Ho + 2) * (Wo + 2) * groups;
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= total) return;
@@ -534,7 +534,7 @@ zero_upsample_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, i
         if (w < 0) w = Wo - 1;
         if (w >= Wo) w = 0;
         const int h = hp - 1;
-        if (h % sh == 0 && w % sw == 0)
+        if (h % sh == 0 && w % sw == 0 && h / sh < H && w / sw < W)
             out = __ldg(reinterpret_cast<const uint4*>(x + ((((size_t)b * (H + 2)) + h / sh + 1) * (W + 2) + w / sw + 1) * C) + g);
     }
     *reinterpret_cast<uint4*>(y + pixel * C + g * 8) = out;
@@ -671,6 +671,20 @@ struct TensorMaps {
     CUtensorMap x, w;
 };
 
+// Output tile of `pixels` (128 fprop / 64 wgrad) = TW x TH with TW a power of two >= 4: the shape that wastes
+// the fewest pixels on a Hout x Wout image (ragged tiles are zero-filled by TMA on the way in and masked
+// on the way out), the widest one on ties.  64x2048 images tile exactly; KITTI's 64x720 (widths 360, 180,
+// 90, 45, 23 down the encoder) pads by 0-7 %.
+static void pick_tile(int Hout, int Wout, int pixels, int* TW, int* TH) {
+    long best = -1;
+    for (int tw = pixels; tw >= 4; tw >>= 1) {
+        const int th = pixels / tw;
+        if (th > 64) break;
+        const long cost = (long)((Wout + tw - 1) / tw) * tw * (long)((Hout + th - 1) / th) * th;
+        if (best < 0 || cost < best) { best = cost; *TW = tw; *TH = th; }
+    }
+}
+
 // Tensor maps depend only on (pointers, shapes); encoding them costs a few microseconds of host time
 // per call, which matters when 20 convolutions are launched back to back.  Small per-thread cache.
 static const TensorMaps* get_maps(const void* x, const void* w, int B, int Hin, int Win, int Cin, int Cout,
@@ -730,17 +744,15 @@ extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void
     DELORA_CHECK_ARG(ksize == 3 || ksize == 1, "delora_conv2d_fprop_bf16: kernel size %d unsupported", ksize);
     DELORA_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0, "delora_conv2d_fprop_bf16: Cin=%d, Cout=%d must be multiples of 64",
                      Cin, Cout);
-    DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin % stride_h == 0 &&
-                         Win % stride_w == 0, "delora_conv2d_fprop_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
+    DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin >= 1 && Win >= 1,
+                     "delora_conv2d_fprop_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
     ConvParams p;
     p.B = B; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
     p.stride_h = stride_h; p.stride_w = stride_w; p.pad_off = (ksize == 1) ? 1 : 0; p.act = act;
-    p.Hout = Hin / stride_h; p.Wout = Win / stride_w;
-    p.TW = p.Wout >= 128 ? 128 : p.Wout;
-    DELORA_CHECK_ARG(128 % p.TW == 0 && p.Wout % p.TW == 0, "delora_conv2d_fprop_bf16: Wout=%d must divide or be divided by 128",
-                     p.Wout);
-    p.TH = 128 / p.TW;
-    p.tiles_w = p.Wout / p.TW;
+    // 3x3 / pad 1 and 1x1 / pad 0 both give floor((n - 1) / stride) + 1 outputs
+    p.Hout = (Hin - 1) / stride_h + 1; p.Wout = (Win - 1) / stride_w + 1;
+    pick_tile(p.Hout, p.Wout, kBlockM, &p.TW, &p.TH);
+    p.tiles_w = (p.Wout + p.TW - 1) / p.TW;
     p.tiles_h = (p.Hout + p.TH - 1) / p.TH;
     p.BN = (Cout % 128 == 0) ? 128 : 64;
     // two CTAs per SM: one CTA's epilogue overlaps the other's main loop (ring = 3 stages of 32 KB for
@@ -787,7 +799,9 @@ static int wgrad_splits(int B, int Hout, int Wout, int Cin, int Cout, int ksize)
     const int base_ctas = ksize * ksize * ((Cout + 127) / 128) * (Cin / (64 * nb));
     int splits = (2 * kNumSMs + base_ctas - 1) / base_ctas;
     splits = splits < 1 ? 1 : (splits > 64 ? 64 : splits);
-    const int k_tiles = (B * Hout * Wout) / 64;
+    int tw = 64, th = 1;
+    pick_tile(Hout, Wout, 64, &tw, &th);
+    const int k_tiles = B * ((Hout + th - 1) / th) * ((Wout + tw - 1) / tw);
     return splits > k_tiles ? (k_tiles > 0 ? k_tiles : 1) : splits;
 }
 
@@ -802,18 +816,15 @@ extern "C" int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw
     DELORA_CHECK_ARG(ksize == 3 || ksize == 1, "delora_conv2d_wgrad_bf16: kernel size %d unsupported", ksize);
     DELORA_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cin_true >= 1 && Cin_true <= Cin,
                      "delora_conv2d_wgrad_bf16: Cin=%d, Cout=%d must be multiples of 64", Cin, Cout);
-    DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin % stride_h == 0 &&
-                         Win % stride_w == 0, "delora_conv2d_wgrad_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
+    DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin >= 1 && Win >= 1,
+                     "delora_conv2d_wgrad_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
     WgradParams p;
     p.B = B; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
     p.stride_h = stride_h; p.stride_w = stride_w; p.pad_off = (ksize == 1) ? 1 : 0;
-    p.Hout = Hin / stride_h; p.Wout = Win / stride_w;
-    p.TW = p.Wout >= 64 ? 64 : p.Wout;
-    DELORA_CHECK_ARG(64 % p.TW == 0 && p.Wout % p.TW == 0 && p.Hout % (64 / p.TW) == 0,
-                     "delora_conv2d_wgrad_bf16: output %dx%d does not tile into 64-pixel blocks", p.Hout, p.Wout);
-    p.TH = 64 / p.TW;
-    p.tiles_per_row = p.Wout / p.TW;
-    p.row_tiles = p.Hout / p.TH;
+    p.Hout = (Hin - 1) / stride_h + 1; p.Wout = (Win - 1) / stride_w + 1;
+    pick_tile(p.Hout, p.Wout, 64, &p.TW, &p.TH);
+    p.tiles_per_row = (p.Wout + p.TW - 1) / p.TW;
+    p.row_tiles = (p.Hout + p.TH - 1) / p.TH;
     p.k_tiles = B * p.row_tiles * p.tiles_per_row;
     p.nb = (Cin >= 256) ? 4 : (Cin / 64);                    // N tile = 64, 128 or 256 input channels
     p.ci_tiles = Cin / (64 * p.nb);
@@ -826,7 +837,9 @@ extern "C" int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw
     CUtensorMap map_dz, map_x;
     {
         const int Hp = p.Hout + 2, Wp = p.Wout + 2;
-        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
+        // extents stop at the last REAL pixel (padded index Wout / Hout): a ragged K tile then reads zeros from
+        // TMA's out-of-bounds fill instead of the circular halo column, so it adds nothing to the sum
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)(Wp - 1), (cuuint64_t)(Hp - 1), (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)Wp * Cout * 2, (cuuint64_t)Hp * Wp * Cout * 2};
         cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -863,12 +876,15 @@ extern "C" int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw
     return 0;
 }
 
-extern "C" int delora_zero_upsample_nhwc_bf16(const void* x, int B, int H, int W, int C, int sh, int sw, void* y,
-                                              void* stream) {
+extern "C" int delora_zero_upsample_nhwc_bf16(const void* x, int B, int H, int W, int C, int sh, int sw, int Hout,
+                                              int Wout, void* y, void* stream) {
     DELORA_CHECK_ARG(x && y && C % 8 == 0 && sh >= 1 && sw >= 1, "delora_zero_upsample_nhwc_bf16: bad argument");
-    const size_t total = (size_t)B * (H * sh + 2) * (W * sw + 2) * (C / 8);
+    DELORA_CHECK_ARG((Hout - 1) / sh + 1 == H && (Wout - 1) / sw + 1 == W,
+                     "delora_zero_upsample_nhwc_bf16: %dx%d is not the stride-(%d,%d) input size of a %dx%d output", Hout,
+                     Wout, sh, sw, H, W);
+    const size_t total = (size_t)B * (Hout + 2) * (Wout + 2) * (C / 8);
     zero_upsample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, B, H, W, C, sh, sw, (__nv_bfloat16*)y);
+        (const __nv_bfloat16*)x, B, H, W, C, sh, sw, Hout, Wout, (__nv_bfloat16*)y);
     DELORA_CHECK_LAUNCH("zero_upsample_kernel");
     return 0;
 }

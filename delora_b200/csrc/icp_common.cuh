@@ -142,6 +142,21 @@ __device__ __forceinline__ void write_warp_partials(const float (&acc)[kIcpAcc],
     if (lane < DELORA_ICP_PARTIAL - 32) row[32 + lane] = keep1;
 }
 
+// same reduction, ADDED to a row that already holds the sums of the other lanes (second kernel of the dense path)
+template <int N = kIcpAcc>
+__device__ __forceinline__ void add_warp_partials(const float (&acc)[kIcpAcc], float* __restrict__ row) {
+    const int lane = threadIdx.x & 31;
+    float keep0 = 0.0f, keep1 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const float s = warp_sum(acc[k]);
+        if (k < 32) { if (lane == k) keep0 = s; }
+        else        { if (lane == k - 32) keep1 = s; }
+    }
+    row[lane] += keep0;
+    if (lane < DELORA_ICP_PARTIAL - 32) row[32 + lane] += keep1;
+}
+
 // scratch layout (floats): [B * rows * 40 partial rows][B * 40 column sums][B int32 counters]
 struct IcpScratch {
     float* rows;

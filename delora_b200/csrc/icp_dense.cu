@@ -14,6 +14,7 @@
 // cells (coalesced, L1-resident), and the guard is the same proof as in icp.cu: all unsearched
 // targets lie beyond a border half-plane (azimuth) or cone (elevation) of the lane's window.
 #include <stdlib.h>
+#include <algorithm>
 #include "icp_common.cuh"
 
 namespace delora {
@@ -91,9 +92,14 @@ __device__ __noinline__ int nn_exact_rescan(const float4* __restrict__ tg, int H
 //     sin^2(theta/2) >= max( sin^2(gap_el/2), cos(e_s) * min cos(e_blk) * sin^2(gap_az/2) )
 // exceeds the current best distance cannot hold the nearest neighbour and is skipped.
 constexpr int kBlkH = 4, kBlkW = 16;
-__device__ unsigned int g_dbg[8];     // phase-2 statistics (owners, blocks tested, blocks scanned, max scanned/owner, warps)
-constexpr int kDefaultMaxStrips = 64; // strip expansions before a lane switches to the block search (measured:
-                                      // 24 -> +25 % on well-aligned pairs from serialised owners, 64 -> +2 %)
+// Search statistics, collected only when flags has DELORA_ICP_STATS (read with delora_icp_stats):
+//  0 warps | 1 strips (warp level) | 2 cells per lane (warp level) | 3 warps entering the block search |
+//  4 owners | 5 blocks tested | 6 blocks scanned | 7 max blocks scanned by one owner | 8 float64 re-rankings |
+//  9 max blocks tested by one owner | 10 owners with > 256 blocks | 11 owners without any candidate so far |
+//  16..23 warps by strip count {0, 1-2, 3-5, 6-10, 11-20, 21-40, 41-63, >= limit} | 24..31 cells per lane, same buckets
+__device__ unsigned int g_dbg[32];
+constexpr int kDefaultMaxStrips = 16; // window-growing steps before a lane is handed to the block-search kernel
+                                      // (measured sweep in DESIGN.md)
 
 __global__ void __launch_bounds__(256)
 block_range_kernel(const float4* __restrict__ grid, int H, int W, int nbh, int nbw, float2* __restrict__ blk) {
@@ -141,43 +147,81 @@ __device__ __forceinline__ void nn2_merge(NN2& a, float bm1, float bm2, int bj) 
     if (take) { a.m1 = bm1; a.j1 = bj; }
 }
 
-template <bool PO2PO>
+// Per-lane source state shared by the two kernels: the transformed source point, its re-projection and
+// the centre cell of its search window.
+struct SrcLane {
+    float4 p, m;                       // source point / normal before the transform
+    float sx, sy, sz, nsx, nsy, nsz;   // after the transform
+    float us, vs, r, rxy;
+    int rc, cc;
+    bool active;
+};
+
+__device__ __forceinline__ SrcLane load_src_lane(const float4* __restrict__ src_grid, const float4* __restrict__ src_ngrid,
+                                                 const float* __restrict__ T, int b, int i, int HW, const GridParams& g) {
+    SrcLane s;
+    s.p = make_float4(0.f, 0.f, 0.f, 0.f);
+    s.m = s.p;
+    s.active = false;
+    if (i < HW) {
+        s.p = __ldg(src_grid + (size_t)b * HW + i);
+        s.active = __float_as_int(s.p.w) >= 0;
+        if (s.active) s.m = __ldg(src_ngrid + (size_t)b * HW + i);
+    }
+    s.sx = s.sy = s.sz = s.nsx = s.nsy = s.nsz = 0.f;
+    if (s.active) {
+        const Rigid rt = load_rigid(T + (size_t)b * 12);
+        apply_rigid(rt, s.p, s.m, s.sx, s.sy, s.sz, s.nsx, s.nsy, s.nsz);
+    }
+    s.us = 0.f; s.vs = 0.f;
+    pixel_coords(g, s.sx, s.sy, s.sz, s.us, s.vs);
+    if (!(s.us == s.us)) s.us = 0.0f;
+    if (!(s.vs == s.vs)) s.vs = 0.0f;
+    s.rxy = sqrtf(fmaf(s.sx, s.sx, s.sy * s.sy));
+    s.r = sqrtf(fmaf(s.sz, s.sz, fmaf(s.sx, s.sx, s.sy * s.sy)));
+    s.cc = (int)fminf(fmaxf(rintf(s.us), 0.0f), g.wm1);
+    s.rc = (int)fminf(fmaxf(rintf(s.vs), 0.0f), g.hm1);
+    return s;
+}
+
+// Work list of the second kernel (in `scratch`): one item per warp of icp_dense_kernel that gave up on
+// some of its lanes after `max_strips` window-growing steps.
+struct PendingList {
+    int* counters;          // [0] number of items, [1] CTAs of the second kernel that have finished; both 0 when idle
+    int4* items;            // (pair, warp in pair, mask of unfinished lanes, 0)
+    float4* state;          // [item][lane]: (m1, m2, bits(j1), 0) of the window search so far
+};
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1: window search for everybody; the (few) lanes whose exactness guard still fails after
+// `max_strips` steps are handed to kernel 2 and contribute nothing to their warp's partial row here.
+// Why two kernels: those lanes are the far-ground points lying between two LiDAR rings of the other
+// scan (NN distance ~ half the ring spacing, metres) and depth discontinuities; ~2-5 % of the warps,
+// but each needs thousands of cells or a serial per-lane block search, and as stragglers inside this
+// kernel they stretched it from ~125 to ~250 us (measured).
+template <bool PO2PO, bool STATS>
 __global__ void __launch_bounds__(kDenseThreads, 8)
 icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__ src_ngrid,
                  const float* __restrict__ T, const float4* __restrict__ tgt_grid,
-                 const float4* __restrict__ tgt_ngrid, const float2* __restrict__ blk_range, int nbh, int nbw,
-                 int max_strips, GridParams g, uint32_t flags, float* __restrict__ partial_rows, int rows_per_pair) {
+                 const float4* __restrict__ tgt_ngrid, int max_strips, GridParams g, uint32_t flags,
+                 float* __restrict__ partial_rows, int rows_per_pair, PendingList pend) {
     const int b = blockIdx.y;
     const int H = g.H, W = g.W, HW = H * W;
     const float4* __restrict__ tg = tgt_grid + (size_t)b * HW;
     const float4* __restrict__ tn = tgt_ngrid + (size_t)b * HW;
     const int i = blockIdx.x * kDenseThreads + threadIdx.x;
     const int warp_in_pair = i >> 5;
+    const int lane = threadIdx.x & 31;
     constexpr float kInf = 3.0e38f;
     constexpr float kSlack = 2e-3f;     // px; covers the fp32 error of the cell binning
 
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), m = p;
-    bool active = false;
-    if (i < HW) {
-        p = __ldg(src_grid + (size_t)b * HW + i);
-        active = __float_as_int(p.w) >= 0;
-        if (active) m = __ldg(src_ngrid + (size_t)b * HW + i);
-    }
-    float sx = 0.f, sy = 0.f, sz = 0.f, nsx = 0.f, nsy = 0.f, nsz = 0.f;
-    if (active) {
-        const Rigid rt = load_rigid(T + (size_t)b * 12);
-        apply_rigid(rt, p, m, sx, sy, sz, nsx, nsy, nsz);
-    }
+    const SrcLane s = load_src_lane(src_grid, src_ngrid, T, b, i, HW, g);
+    const bool active = s.active;
+    const float sx = s.sx, sy = s.sy, sz = s.sz;
     int best_j = -1;
     if (__ballot_sync(0xffffffffu, active) != 0u) {
-        float us = 0.f, vs = 0.f;
-        pixel_coords(g, sx, sy, sz, us, vs);
-        if (!(us == us)) us = 0.0f;
-        if (!(vs == vs)) vs = 0.0f;
-        const float rxy = sqrtf(fmaf(sx, sx, sy * sy));
-        const float r = sqrtf(fmaf(sz, sz, fmaf(sx, sx, sy * sy)));
-        const int cc = (int)fminf(fmaxf(rintf(us), 0.0f), g.wm1);
-        const int rc = (int)fminf(fmaxf(rintf(vs), 0.0f), g.hm1);
+        const float us = s.us, vs = s.vs, r = s.r, rxy = s.rxy;
+        const int rc = s.rc, cc = s.cc;
         // distance (px) from the source direction to the four borders of its own centre cell
         const float f_dn = (vs - (float)rc) + 0.5f - kSlack, f_up = ((float)rc - vs) + 0.5f - kSlack;
         const float f_lf = (us - (float)cc) + 0.5f - kSlack, f_rt = ((float)cc - us) + 0.5f - kSlack;
@@ -187,8 +231,6 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
         // warp-uniform window extents around every lane's own (rc, cc); the 3 x 5 start window is
         // fully unrolled: 15 independent loads in flight
         int e_dn = 1, e_up = 1, e_lf = 2, e_rt = 2;
-        bool ext_private = false;      // set for lanes whose extents were widened by the block search
-        (void)ext_private;
         if (H >= 3 && W >= 5) {
             int col[5];
 #pragma unroll
@@ -199,7 +241,8 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
                 const bool rok = active && row >= 0 && row < H;
                 const int rbase = min(max(row, 0), H - 1) * W;          // always a valid address
 #pragma unroll
-                for (int dc = 0; dc < 5; ++dc) nn2_eval(__ldg(tg + rbase + col[dc]), rbase + col[dc], sx, sy, sz, nn, rok);
+                for (int dc = 0; dc < 5; ++dc)   // unsigned index: one IMAD.WIDE.U32 instead of a 4-instruction sign-extending LEA chain
+                    nn2_eval(__ldg(tg + (unsigned)(rbase + col[dc])), rbase + col[dc], sx, sy, sz, nn, rok);
             }
         } else {
             e_dn = e_up = e_lf = e_rt = 0;
@@ -212,7 +255,8 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
                    : border_bound(f_lf + (float)e_lf - (cc - e_lf <= 0 ? g.seam_px : 0.0f), g.du_rad, rxy);
         float b_rt = (e_lf + e_rt + 1 >= W) ? kInf
                    : border_bound(f_rt + (float)e_rt - (cc + e_rt >= W - 1 ? g.seam_px : 0.0f), g.du_rad, rxy);
-        unsigned pending = 0u;                                   // lanes that still fail after kMaxStrips strips
+        unsigned pending = 0u;                                   // lanes that still fail after max_strips steps
+        int n_strips = 0, n_cells = 15;
         for (int strip = 0;; ++strip) {
             const float bmin = fminf(fminf(b_dn, b_up), fminf(b_lf, b_rt));
             const bool done = !active || bmin >= kInf ||
@@ -220,6 +264,7 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
             const unsigned failing = __ballot_sync(0xffffffffu, !done);
             if (failing == 0u) break;
             if (strip >= max_strips) { pending = failing; break; }
+            if (STATS) n_strips = strip + 1;
             const int my_side = (bmin == b_dn) ? 0 : (bmin == b_up) ? 1 : (bmin == b_lf) ? 2 : 3;
             const int side = __shfl_sync(0xffffffffu, my_side, __ffs(failing) - 1);
             if (side < 2) {
@@ -227,10 +272,11 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
                 const bool rok = active && row >= 0 && row < H;
                 const int rbase = min(max(row, 0), H - 1) * W;
                 const int n = e_lf + e_rt + 1;
+                if (STATS) n_cells += n;
                 int col = wrap_col(cc - e_lf, W);
 #pragma unroll 4
                 for (int k = 0; k < n; ++k) {
-                    nn2_eval(__ldg(tg + rbase + col), rbase + col, sx, sy, sz, nn, rok);
+                    nn2_eval(__ldg(tg + (unsigned)(rbase + col)), rbase + col, sx, sy, sz, nn, rok);
                     ++col;
                     col = (col == W) ? 0 : col;
                 }
@@ -241,14 +287,15 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
                 const int c0 = wrap_col((side == 2) ? cc - e_lf - 1 : cc + e_rt + 1, W);
                 const int c1 = wrap_col((side == 2) ? cc - e_lf - 2 : cc + e_rt + 2, W);
                 const int n = e_dn + e_up + 1;
+                if (STATS) n_cells += 2 * n;
                 const bool two = (step == 2);
 #pragma unroll 2
                 for (int k = 0; k < n; ++k) {
                     const int row = rc - e_dn + k;
                     const bool rok = active && row >= 0 && row < H;
                     const int rbase = min(max(row, 0), H - 1) * W;
-                    nn2_eval(__ldg(tg + rbase + c0), rbase + c0, sx, sy, sz, nn, rok);
-                    nn2_eval(__ldg(tg + rbase + c1), rbase + c1, sx, sy, sz, nn, rok && two);
+                    nn2_eval(__ldg(tg + (unsigned)(rbase + c0)), rbase + c0, sx, sy, sz, nn, rok);
+                    nn2_eval(__ldg(tg + (unsigned)(rbase + c1)), rbase + c1, sx, sy, sz, nn, rok && two);
                 }
                 if (side == 2) e_lf += step; else e_rt += step;
                 const bool full_w = (e_lf + e_rt + 1 >= W);
@@ -256,19 +303,197 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
                 b_rt = full_w ? kInf : border_bound(f_rt + (float)e_rt - (cc + e_rt >= W - 1 ? g.seam_px : 0.0f), g.du_rad, rxy);
             }
         }
-        // ---------------- phase 2: warp-cooperative, range-pruned block search for the remaining lanes
+        if (STATS && lane == 0) {
+            const int bucket = pending ? 7 : n_strips == 0 ? 0 : n_strips <= 2 ? 1 : n_strips <= 5 ? 2 : n_strips <= 10 ? 3
+                             : n_strips <= 20 ? 4 : n_strips <= 40 ? 5 : 6;
+            atomicAdd(&g_dbg[0], 1u); atomicAdd(&g_dbg[1], (unsigned)n_strips); atomicAdd(&g_dbg[2], (unsigned)n_cells);
+            atomicAdd(&g_dbg[16 + bucket], 1u); atomicAdd(&g_dbg[24 + bucket], (unsigned)n_cells);
+            if (pending) atomicAdd(&g_dbg[3], 1u);
+        }
+        if (pending) {
+            // hand the unfinished lanes to kernel 2 (the order of the items is arbitrary, but every item owns
+            // its warp's partial row, so the sums stay deterministic)
+            int item = 0;
+            if (lane == 0) {
+                item = atomicAdd(pend.counters, 1);
+                pend.items[item] = make_int4(b, warp_in_pair, (int)pending, 0);
+            }
+            item = __shfl_sync(0xffffffffu, item, 0);
+            pend.state[(size_t)item * 32 + lane] = make_float4(nn.m1, nn.m2, __int_as_float(nn.j1), 0.0f);
+        }
+        best_j = ((pending >> lane) & 1u) ? -1 : nn.j1;
+        if (active && best_j >= 0 && nn.m2 <= nn.m1 * (1.0f + kNNBand)) {
+            if (STATS) atomicAdd(&g_dbg[8], 1u);
+            best_j = nn_exact_rescan(tg, H, W, rc, cc, e_dn, e_up, e_lf, e_rt, sx, sy, sz, nn.m1 * (1.0f + kNNBand));
+        }
+    }
+    float acc[kIcpAcc];
+#pragma unroll
+    for (int k = 0; k < kIcpAcc; ++k) acc[k] = 0.0f;
+    if (active && best_j >= 0) {
+        float4 pd, nd;
+        accumulate_pair(PO2PO ? flags : (flags & ~DELORA_LOSS_PO2PO), s.p, s.m, sx, sy, sz, s.nsx, s.nsy, s.nsz,
+                        __ldg(tg + best_j), __ldg(tn + best_j), acc, pd, nd);
+    }
+    if (warp_in_pair < rows_per_pair)
+        write_warp_partials<(PO2PO ? kIcpAcc : 24)>(
+            acc, partial_rows + ((size_t)b * rows_per_pair + warp_in_pair) * DELORA_ICP_PARTIAL);
+}
+
+struct OwnerGeom { float sx, sy, sz, us, vs, r, cos_es; };
+struct BlockRect { int br_lo, bc_lo, nbc, nblk; };       // bc_lo unwrapped; nbc columns x (nblk / nbc) rows of blocks
+
+// One pass of a warp over the blocks of `rect` for one source point: 32 blocks are bounded at a time (one per
+// lane), the blocks whose lower bound does not exceed `bound` are scanned, 2 cells per lane.
+//   EXACT = false: fp32 (smallest, second smallest) tracking in `loc`; `bound` tightens as candidates are found.
+//   EXACT = true : `bound` is the fixed tie threshold; candidates inside it are ranked in float64 (ebest, ej).
+// Returns the number of blocks scanned.
+template <bool EXACT>
+__device__ __forceinline__ int block_pass(const float4* __restrict__ tg, const float2* __restrict__ blk,
+                                          const GridParams& g, int nbw, const OwnerGeom& o, const BlockRect& rect,
+                                          float& bound, NN2& loc, double& ebest, int& ej) {
+    constexpr float kInf = 3.0e38f;
+    constexpr float kSlack = 2e-3f;
+    const int H = g.H, W = g.W;
+    const int lane = threadIdx.x & 31;
+    int scanned = 0;
+    for (int base = 0; base < rect.nblk; base += 32) {
+        const int idx = base + lane;
+        const bool in = idx < rect.nblk;
+        const int br = rect.br_lo + (in ? idx / rect.nbc : 0);
+        int bc = rect.bc_lo + (in ? idx % rect.nbc : 0);
+        bc += (bc < 0) ? nbw : 0;
+        bc -= (bc >= nbw) ? nbw : 0;
+        bool ok = in;
+        float lb2 = kInf;
+        if (ok) {
+            const float2 rg = __ldg(blk + br * nbw + bc);
+            if (rg.y >= 0.0f) {
+                const float v_lo = (float)(br * kBlkH) - 0.5f, v_hi = (float)min(br * kBlkH + kBlkH - 1, H - 1) + 0.5f;
+                const float u_lo = (float)(bc * kBlkW) - 0.5f, u_hi = (float)min(bc * kBlkW + kBlkW - 1, W - 1) + 0.5f;
+                const float gv = fmaxf(fmaxf(v_lo - o.vs, o.vs - v_hi) - kSlack, 0.0f) * g.dv_rad;
+                // azimuth gap ON THE CIRCLE: the direct way, or the other way round through the seam
+                const float d1 = u_lo - o.us, d2 = o.us - u_hi;
+                const float gpx = fminf(fmaxf(fmaxf(d1, d2), 0.0f), g.circ_px + fminf(d1, d2));
+                const float gu = fmaxf(gpx - kSlack, 0.0f) * g.du_rad;
+                const float sv = __sinf(fminf(0.5f * gv, kHalfPiF)), su = __sinf(fminf(0.5f * gu, kHalfPiF));
+                const float e_lo = g.vf0 + v_lo * g.dv_rad, e_hi = g.vf0 + v_hi * g.dv_rad;
+                const float c_blk = fmaxf(fminf(__cosf(e_lo), __cosf(e_hi)), 0.0f);
+                const float S = fmaxf(sv * sv, o.cos_es * c_blk * su * su);
+                const float rho = fminf(fmaxf(o.r * (1.0f - 2.0f * S), rg.x), rg.y);
+                const float dr_ = o.r - rho;
+                lb2 = fmaf(dr_, dr_, 4.0f * o.r * rho * S) * 0.999f;
+            } else {
+                ok = false;                                       // empty block
+            }
+        }
+        unsigned need = __ballot_sync(0xffffffffu, ok && lb2 <= bound * 1.001f);
+        scanned += __popc(need);
+        while (need) {
+            const int sel = __ffs(need) - 1;
+            need &= need - 1;
+            const int sbr = __shfl_sync(0xffffffffu, br, sel), sbc = __shfl_sync(0xffffffffu, bc, sel);
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int c = lane + 32 * h2;
+                const int row = sbr * kBlkH + (c >> 4), col = sbc * kBlkW + (c & 15);
+                const bool cok = row < H && col < W;
+                const int j = min(row, H - 1) * W + min(col, W - 1);
+                const float4 t = __ldg(tg + j);
+                if (!EXACT) {
+                    nn2_eval(t, j, o.sx, o.sy, o.sz, loc, cok);
+                } else {
+                    const float dx = o.sx - t.x, dy = o.sy - t.y, dz = o.sz - t.z;
+                    const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (cok && d2f <= bound) {
+                        const double d2e = nn_d2_exact(o.sx, o.sy, o.sz, t.x, t.y, t.z);
+                        if (d2e < ebest || (d2e == ebest && j < ej)) { ebest = d2e; ej = j; }
+                    }
+                }
+            }
+        }
+        if (!EXACT) {   // tighten the running best with what this chunk found (prunes the following chunks harder)
+            float wm = loc.m1;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) wm = fminf(wm, __shfl_xor_sync(0xffffffffu, wm, s));
+            bound = fminf(bound, wm);
+        }
+    }
+    return scanned;
+}
+
+// rare path, kept out of line so that its float64 registers do not count against the search loop
+__device__ __noinline__ int exact_rerank_warp(const float4* __restrict__ tg, const float2* __restrict__ blk,
+                                              const GridParams& g, int nbw, const OwnerGeom& o, const BlockRect& rect,
+                                              float thresh) {
+    double ebest = 1.0e300;
+    int ej = 0x7fffffff;
+    NN2 unused;
+    unused.m1 = unused.m2 = 3.0e38f; unused.j1 = -1;
+    block_pass<true>(tg, blk, g, nbw, o, rect, thresh, unused, ebest, ej);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, ebest, s);
+        const int oj = __shfl_xor_sync(0xffffffffu, ej, s);
+        if (ob < ebest || (ob == ebest && oj < ej)) { ebest = ob; ej = oj; }
+    }
+    return ej;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 2: range-pruned block search for the lanes kernel 1 gave up on.  One CTA per item (= one warp of
+// kernel 1); its unfinished lanes ("owners") are dealt round-robin to the CTA's warps, and a whole warp
+// searches for ONE owner: 32 lanes bound 32 blocks of the certifying rectangle at a time and scan the
+// blocks that survive, 32 cells per step.  Warp 0 then adds the owners' loss / gradient terms to the partial
+// row kernel 1 wrote for that warp (fixed order: deterministic).  Persistent grid; the last CTA re-arms
+// the work list.
+constexpr int kPendThreads = 256;
+
+template <bool PO2PO, bool STATS>
+__global__ void __launch_bounds__(kPendThreads, 4)
+icp_dense_pending_kernel(const float4* __restrict__ src_grid, const float4* __restrict__ src_ngrid,
+                         const float* __restrict__ T, const float4* __restrict__ tgt_grid,
+                         const float4* __restrict__ tgt_ngrid, const float2* __restrict__ blk_range, int nbh, int nbw,
+                         GridParams g, uint32_t flags, float* __restrict__ partial_rows, int rows_per_pair,
+                         PendingList pend) {
+    __shared__ int s_res[32];         // per owner lane: pixel id of its nearest neighbour (-1: none)
+    __shared__ float4 s_pos[32], s_uv[32];   // (sx, sy, sz, |s|), (u, v, |s_xy|, m1)
+    __shared__ int4 s_cell[32];              // (centre row, centre column, bits(m2), j1)
+    const int H = g.H, W = g.W, HW = H * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kWarps = (int)blockDim.x >> 5;
+    constexpr float kInf = 3.0e38f;
+    constexpr float kSlack = 2e-3f;
+    const int n_items = *reinterpret_cast<volatile int*>(pend.counters);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int4 it = pend.items[item];
+        const int b = it.x, warp_in_pair = it.y;
+        const unsigned pending = (unsigned)it.z;
+        const float4* __restrict__ tg = tgt_grid + (size_t)b * HW;
+        const float4* __restrict__ tn = tgt_ngrid + (size_t)b * HW;
         const float2* __restrict__ blk = blk_range + (size_t)b * nbh * nbw;
-        const int lane = threadIdx.x & 31;
-        if (pending && (threadIdx.x & 31) == 0) { atomicAdd(&g_dbg[5], 1u); atomicMax(&g_dbg[6], (unsigned)__popc(pending)); }
-        while (pending) {
-            const int owner = __ffs(pending) - 1;
-            pending &= pending - 1;
-            const float osx = __shfl_sync(0xffffffffu, sx, owner), osy = __shfl_sync(0xffffffffu, sy, owner),
-                        osz = __shfl_sync(0xffffffffu, sz, owner);
-            const float ous = __shfl_sync(0xffffffffu, us, owner), ovs = __shfl_sync(0xffffffffu, vs, owner);
-            const float orr = __shfl_sync(0xffffffffu, r, owner), orxy = __shfl_sync(0xffffffffu, rxy, owner);
-            const int orc = __shfl_sync(0xffffffffu, rc, owner), occ = __shfl_sync(0xffffffffu, cc, owner);
-            float obest = __shfl_sync(0xffffffffu, nn.m1, owner);         // running best d^2 (fp32), warp-uniform
+        // warp 0 rebuilds the 32 lanes of the item (transform, re-projection, search state) and shares them
+        // through shared memory; every warp then reads the lanes it searches for (broadcast reads, no shuffles)
+        SrcLane s;
+        if (warp == 0) {
+            s = load_src_lane(src_grid, src_ngrid, T, b, warp_in_pair * 32 + lane, HW, g);
+            const float4 st = pend.state[(size_t)item * 32 + lane];
+            s_pos[lane] = make_float4(s.sx, s.sy, s.sz, s.r);
+            s_uv[lane] = make_float4(s.us, s.vs, s.rxy, st.x);
+            s_cell[lane] = make_int4(s.rc, s.cc, __float_as_int(st.y), __float_as_int(st.z));
+        }
+        __syncthreads();
+        const int n_owners = __popc(pending);
+        for (int k = warp; k < n_owners; k += kWarps) {
+            const int owner = __fns(pending, 0, k + 1);                  // k-th unfinished lane
+            const float4 opos = s_pos[owner], ouv = s_uv[owner];
+            const int4 ocell = s_cell[owner];
+            const float osx = opos.x, osy = opos.y, osz = opos.z, orr = opos.w;
+            const float ous = ouv.x, ovs = ouv.y, orxy = ouv.z;
+            const int orc = ocell.x, occ = ocell.y;
+            NN2 nn;                                                      // the owner's window-search result
+            nn.m1 = ouv.w; nn.m2 = __int_as_float(ocell.z); nn.j1 = ocell.w;
+            float obest = nn.m1;                                         // running best d^2 (fp32), warp-uniform
             const int obr = orc / kBlkH, obc = occ / kBlkW;
             const float cos_es = orr > 0.0f ? orxy / orr : 1.0f;
             NN2 loc;
@@ -276,6 +501,7 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
             // Block rectangle that certifies the CURRENT best: grow it (warp-uniform scalar loops) until all
             // four borders are at least d0 away; the best can only shrink while the rectangle is scanned, so
             // one pass over its blocks is enough (no ring-by-ring dependency chain).
+            const float obest0 = obest;
             const float d0 = (obest < kInf) ? sqrtf(obest) * (1.00001f / 0.9995f) : kInf;
             int br_lo = obr, br_hi = obr, bc_lo = obc, bc_hi = obc;            // bc_* unwrapped
             while (br_lo > 0 && border_bound(ovs - ((float)(br_lo * kBlkH) - 0.5f) - kSlack, g.dv_rad, orr) < d0) --br_lo;
@@ -291,103 +517,83 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
                    border_bound(((float)blk_u_hi(bc_hi, nbw, W) + 0.5f) - ous - kSlack - (bc_hi >= nbw - 1 ? g.seam_px : 0.0f),
                                 g.du_rad, orxy) < d0) ++bc_hi;
             const int nbc = bc_hi - bc_lo + 1, nblk = (br_hi - br_lo + 1) * nbc;
-            int dbg_scanned = 0;
-            for (int base = 0; base < nblk; base += 32) {
-                const int idx = base + lane;
-                const bool in = idx < nblk;
-                const int br = br_lo + (in ? idx / nbc : 0);
-                int bc = bc_lo + (in ? idx % nbc : 0);
-                bc += (bc < 0) ? nbw : 0;
-                bc -= (bc >= nbw) ? nbw : 0;
-                bool ok = in;
-                float lb2 = kInf;
-                if (ok) {
-                    const float2 rg = __ldg(blk + br * nbw + bc);
-                    if (rg.y >= 0.0f) {
-                        const float v_lo = (float)(br * kBlkH) - 0.5f, v_hi = (float)min(br * kBlkH + kBlkH - 1, H - 1) + 0.5f;
-                        const float u_lo = (float)(bc * kBlkW) - 0.5f, u_hi = (float)min(bc * kBlkW + kBlkW - 1, W - 1) + 0.5f;
-                        const float gv = fmaxf(fmaxf(v_lo - ovs, ovs - v_hi) - kSlack, 0.0f) * g.dv_rad;
-                        // azimuth gap ON THE CIRCLE: the direct way, or the other way round through the seam
-                        const float d1 = u_lo - ous, d2 = ous - u_hi;
-                        const float gpx = fminf(fmaxf(fmaxf(d1, d2), 0.0f), g.circ_px + fminf(d1, d2));
-                        const float gu = fmaxf(gpx - kSlack, 0.0f) * g.du_rad;
-                        const float sv = __sinf(fminf(0.5f * gv, kHalfPiF)), su = __sinf(fminf(0.5f * gu, kHalfPiF));
-                        const float e_lo = g.vf0 + v_lo * g.dv_rad, e_hi = g.vf0 + v_hi * g.dv_rad;
-                        const float c_blk = fmaxf(fminf(__cosf(e_lo), __cosf(e_hi)), 0.0f);
-                        const float S = fmaxf(sv * sv, cos_es * c_blk * su * su);
-                        const float rho = fminf(fmaxf(orr * (1.0f - 2.0f * S), rg.x), rg.y);
-                        const float dr_ = orr - rho;
-                        lb2 = fmaf(dr_, dr_, 4.0f * orr * rho * S) * 0.999f;
-                    } else {
-                        ok = false;                                       // empty block
-                    }
-                }
-                unsigned need = __ballot_sync(0xffffffffu, ok && lb2 <= obest * 1.001f);
-                dbg_scanned += __popc(need);
-                while (need) {
-                    const int sel = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int sbr = __shfl_sync(0xffffffffu, br, sel), sbc = __shfl_sync(0xffffffffu, bc, sel);
-#pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {
-                        const int c = lane + 32 * h2;
-                        const int row = sbr * kBlkH + (c >> 4), col = sbc * kBlkW + (c & 15);
-                        const bool cok = row < H && col < W;
-                        const int j = min(row, H - 1) * W + min(col, W - 1);
-                        nn2_eval(__ldg(tg + j), j, osx, osy, osz, loc, cok);
-                    }
-                }
-                // tighten the running best with what this chunk found (prunes the following chunks harder)
-                float wm = loc.m1;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) wm = fminf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-                obest = fminf(obest, wm);
+            const OwnerGeom og = {osx, osy, osz, ous, ovs, orr, cos_es};
+            const BlockRect rect = {br_lo, bc_lo, nbc, nblk};
+            double unused_d = 0.0;
+            int unused_j = 0;
+            const int dbg_scanned = block_pass<false>(tg, blk, g, nbw, og, rect, obest, loc, unused_d, unused_j);
+            if (STATS && lane == 0) {
+                atomicAdd(&g_dbg[4], 1u); atomicAdd(&g_dbg[5], (unsigned)nblk); atomicAdd(&g_dbg[6], (unsigned)dbg_scanned);
+                atomicMax(&g_dbg[7], (unsigned)dbg_scanned);
+                atomicMax(&g_dbg[9], (unsigned)nblk);
+                if (nblk > 256) atomicAdd(&g_dbg[10], 1u);
+                if (!(obest0 < kInf)) atomicAdd(&g_dbg[11], 1u);
             }
-            if (lane == 0) {
-                atomicAdd(&g_dbg[0], 1u); atomicAdd(&g_dbg[1], (unsigned)nblk); atomicAdd(&g_dbg[2], (unsigned)dbg_scanned);
-                atomicMax(&g_dbg[3], (unsigned)dbg_scanned); atomicMax(&g_dbg[4], (unsigned)nblk);
-            }
-            // merge the 32 partial results, then into the owner's own phase-1 result
+            // merge the 32 partial results, then into the owner's own window-search result
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const float bm1 = __shfl_xor_sync(0xffffffffu, loc.m1, o), bm2 = __shfl_xor_sync(0xffffffffu, loc.m2, o);
                 const int bj = __shfl_xor_sync(0xffffffffu, loc.j1, o);
                 nn2_merge(loc, bm1, bm2, bj);
             }
-            if (lane == owner) {
-                nn2_merge(nn, loc.m1, loc.m2, loc.j1);
-                // extents of everything that has been examined (for the float64 tie re-ranking)
-                e_dn = max(e_dn, rc - br_lo * kBlkH);
-                e_up = max(e_up, min(br_hi * kBlkH + kBlkH - 1, H - 1) - rc);
-                e_lf = max(e_lf, min(cc - blk_u_lo(bc_lo, nbw, W), W - 1));
-                e_rt = max(e_rt, min(blk_u_hi(bc_hi, nbw, W) - cc, W - 1));
-                ext_private = true;
+            NN2 fin = nn;
+            nn2_merge(fin, loc.m1, loc.m2, loc.j1);
+            const float fm1 = __shfl_sync(0xffffffffu, fin.m1, 0), fm2 = __shfl_sync(0xffffffffu, fin.m2, 0);
+            int fj = __shfl_sync(0xffffffffu, fin.j1, 0);
+            if (fj >= 0 && fm2 <= fm1 * (1.0f + kNNBand)) {
+                // Two candidates inside the fp32 ambiguity band: float64 re-ranking (cKDTree's order) by the whole
+                // warp, over the blocks of the certified rectangle whose lower bound reaches into the band (every
+                // candidate of the band lies inside that rectangle: all cells outside it are farther than d0).
+                if (STATS && lane == 0) atomicAdd(&g_dbg[8], 1u);
+                const float thresh = fm1 * (1.0f + kNNBand);
+                const int ej = exact_rerank_warp(tg, blk, g, nbw, og, rect, thresh);
+                fj = (ej == 0x7fffffff) ? fj : ej;
             }
+            if (lane == 0) s_res[owner] = fj;
         }
-        best_j = nn.j1;
-        if (active && best_j >= 0 && nn.m2 <= nn.m1 * (1.0f + kNNBand))
-            best_j = nn_exact_rescan(tg, H, W, rc, cc, e_dn, e_up, e_lf, e_rt, sx, sy, sz, nn.m1 * (1.0f + kNNBand));
-    }
-    float acc[kIcpAcc];
+        __syncthreads();
+        if (warp == 0) {
+            const bool mine = ((pending >> lane) & 1u) != 0u && s.active;
+            const int best_j = mine ? s_res[lane] : -1;
+            float acc[kIcpAcc];
 #pragma unroll
-    for (int k = 0; k < kIcpAcc; ++k) acc[k] = 0.0f;
-    if (active && best_j >= 0) {
-        float4 pd, nd;
-        accumulate_pair(PO2PO ? flags : (flags & ~DELORA_LOSS_PO2PO), p, m, sx, sy, sz, nsx, nsy, nsz,
-                        __ldg(tg + best_j), __ldg(tn + best_j), acc, pd, nd);
+            for (int k = 0; k < kIcpAcc; ++k) acc[k] = 0.0f;
+            if (mine && best_j >= 0) {
+                float4 pd, nd;
+                accumulate_pair(PO2PO ? flags : (flags & ~DELORA_LOSS_PO2PO), s.p, s.m, s.sx, s.sy, s.sz, s.nsx, s.nsy,
+                                s.nsz, __ldg(tg + best_j), __ldg(tn + best_j), acc, pd, nd);
+            }
+            if (warp_in_pair < rows_per_pair)
+                add_warp_partials<(PO2PO ? kIcpAcc : 24)>(
+                    acc, partial_rows + ((size_t)b * rows_per_pair + warp_in_pair) * DELORA_ICP_PARTIAL);
+        }
+        __syncthreads();                // s_res is reused by the next item
     }
-    if (warp_in_pair < rows_per_pair)
-        write_warp_partials<(PO2PO ? kIcpAcc : 24)>(
-            acc, partial_rows + ((size_t)b * rows_per_pair + warp_in_pair) * DELORA_ICP_PARTIAL);
+    // re-arm the work list: the last CTA to get here has seen every other CTA finish
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(pend.counters + 1, 1) == (int)gridDim.x - 1) {
+            pend.counters[0] = 0;
+            pend.counters[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 }  // namespace delora
 
 using namespace delora;
 
-extern "C" int delora_debug_counters(unsigned int* out8, int reset) {
-    if (out8) cudaMemcpyFromSymbol(out8, delora::g_dbg, 8 * sizeof(unsigned int));
-    if (reset) { unsigned int z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(delora::g_dbg, z, sizeof(z)); }
+extern "C" int delora_icp_stats(uint32_t* out32, int reset) {
+    if (out32) {
+        const cudaError_t e = cudaMemcpyFromSymbol(out32, delora::g_dbg, 32 * sizeof(unsigned int));
+        DELORA_CHECK_ARG(e == cudaSuccess, "delora_icp_stats: %s", cudaGetErrorString(e));
+    }
+    if (reset) {
+        const unsigned int z[32] = {0};
+        const cudaError_t e = cudaMemcpyToSymbol(delora::g_dbg, z, sizeof(z));
+        DELORA_CHECK_ARG(e == cudaSuccess, "delora_icp_stats: %s", cudaGetErrorString(e));
+    }
     return 0;
 }
 
@@ -406,24 +612,44 @@ extern "C" int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_
     cudaStream_t st = (cudaStream_t)stream;
     int max_strips = kDefaultMaxStrips;
     if (const char* e = getenv("DELORA_ICP_MAX_STRIPS")) max_strips = atoi(e);      // tuning knob (tests / profiling)
-    // range pyramid of the TARGET grids, kept behind the partial rows / column sums / counters of the scratch
+    // scratch behind the partial rows / column sums / counters: the range pyramid of the TARGET grids, then the
+    // work list of the second kernel (see delora_icp_scratch_floats)
     const int nbh = (H + kBlkH - 1) / kBlkH, nbw = (W + kBlkW - 1) / kBlkW;
-    float2* blk = reinterpret_cast<float2*>(scratch + (size_t)B * delora_icp_partial_rows(HW) * DELORA_ICP_PARTIAL +
-                                            (size_t)B * DELORA_ICP_PARTIAL + (((size_t)B + 1) & ~(size_t)1));
+    size_t off = (size_t)B * rows * DELORA_ICP_PARTIAL + (size_t)B * DELORA_ICP_PARTIAL + (((size_t)B + 1) & ~(size_t)1);
+    float2* blk = reinterpret_cast<float2*>(scratch + off);
+    off += (size_t)B * 2 * ((size_t)HW / 16 + 4096);
+    off = (off + 3) & ~(size_t)3;                      // 16-byte alignment
+    PendingList pend;
+    pend.counters = reinterpret_cast<int*>(scratch + off);
+    pend.items = reinterpret_cast<int4*>(scratch + off + 4);
+    pend.state = reinterpret_cast<float4*>(scratch + off + 4 + (size_t)4 * B * rows);
     {
         dim3 gb((nbh * nbw * 32 + 255) / 256, B);
         block_range_kernel<<<gb, 256, 0, st>>>((const float4*)tgt_grid, H, W, nbh, nbw, blk);
         DELORA_CHECK_LAUNCH("block_range_kernel");
     }
-    if (flags & DELORA_LOSS_PO2PO) {
-        icp_dense_kernel<true><<<grid, kDenseThreads, 0, st>>>((const float4*)src_grid, (const float4*)src_ngrid, T,
-                                                               (const float4*)tgt_grid, (const float4*)tgt_ngrid, blk,
-                                                               nbh, nbw, max_strips, g, flags, sc.rows, rows);
-    } else {
-        icp_dense_kernel<false><<<grid, kDenseThreads, 0, st>>>((const float4*)src_grid, (const float4*)src_ngrid, T,
-                                                                (const float4*)tgt_grid, (const float4*)tgt_ngrid, blk,
-                                                                nbh, nbw, max_strips, g, flags, sc.rows, rows);
-    }
-    DELORA_CHECK_LAUNCH("icp_dense_kernel");
+    // persistent second kernel: enough CTAs for one wave, never more than there can be items
+    int pend_threads = kPendThreads, pend_mult = 4;
+    if (const char* e = getenv("DELORA_ICP_PEND_THREADS")) pend_threads = atoi(e);   // tuning knobs (profiling only)
+    if (const char* e = getenv("DELORA_ICP_PEND_MULT")) pend_mult = atoi(e);
+    DELORA_CHECK_ARG(pend_threads >= 32 && pend_threads <= 256 && pend_threads % 32 == 0 && pend_mult >= 1,
+                     "DELORA_ICP_PEND_THREADS / DELORA_ICP_PEND_MULT out of range");
+    const int pend_grid = (int)std::min<long long>((long long)B * rows, (long long)pend_mult * kNumSMs);
+#define DELORA_LAUNCH_DENSE(PO2PO, STATS)                                                                           \
+    do {                                                                                                            \
+        icp_dense_kernel<PO2PO, STATS><<<grid, kDenseThreads, 0, st>>>(                                             \
+            (const float4*)src_grid, (const float4*)src_ngrid, T, (const float4*)tgt_grid, (const float4*)tgt_ngrid, \
+            max_strips, g, flags, sc.rows, rows, pend);                                                             \
+        icp_dense_pending_kernel<PO2PO, STATS><<<pend_grid, pend_threads, 0, st>>>(                                 \
+            (const float4*)src_grid, (const float4*)src_ngrid, T, (const float4*)tgt_grid, (const float4*)tgt_ngrid, \
+            blk, nbh, nbw, g, flags, sc.rows, rows, pend);                                                          \
+    } while (0)
+    const bool po2po = (flags & DELORA_LOSS_PO2PO) != 0u, stats = (flags & DELORA_ICP_STATS) != 0u;
+    if (po2po && stats) DELORA_LAUNCH_DENSE(true, true);
+    else if (po2po) DELORA_LAUNCH_DENSE(true, false);
+    else if (stats) DELORA_LAUNCH_DENSE(false, true);
+    else DELORA_LAUNCH_DENSE(false, false);
+#undef DELORA_LAUNCH_DENSE
+    DELORA_CHECK_LAUNCH("icp_dense_kernel / icp_dense_pending_kernel");
     return launch_icp_finalize(scratch, B, rows, lambda_po2pl, flags, losses, grad_T, st);
 }

@@ -1,4 +1,4 @@
-"""Encoder forward on the tcgen05 convolution kernels (inference / no-grad path).
+"""Encoder forward and backward on the tcgen05 convolution kernels.
 
 Takes the weights of an `OdometryModel` (reference parameter names) and runs
 `ResNetModified._forward_impl` (reference: src/models/resnet_modified.py:95-120, BasicBlock :159-177)
@@ -7,9 +7,10 @@ circular-W / zero-H padding: stem 3x3 s(1,2) + tanh, 3x3/(1,2) max-pool, 4 stage
 (second conv fuses residual add + activation, 1x1 strided downsample convs), then average pool,
 `fc` and the two MLP heads (tiny GEMMs, left to torch as SURVEY.md §7.6 allows).
 
-Training still differentiates through the torch/cuDNN path (dgrad/wgrad kernels are the next
-milestone); this class is what inference (`inference_only`, Tester / ROS node shape, BASELINE
-config #5) and the encoder benchmark use.
+Training (`pooled_features`, an autograd Function) keeps the activations and runs the backward as
+dgrad (the same fprop kernel on the output gradient with flipped filters, act' fused in the epilogue)
+and wgrad (split-K over pixels) launches.  Any image size works (ragged tiles are zero-filled /
+masked): 64x2048 tiles exactly, KITTI's 64x720 runs 360 -> 180 -> 90 -> 45 -> 23 wide.
 """
 import torch
 
@@ -84,7 +85,7 @@ class TensorCoreEncoder:
         b, _, h, w = image_1.shape
         dev = image_1.device
         x = ops.images_to_nhwc(image_1.float().contiguous(), image_2.float().contiguous(), 64)
-        w2 = w // 2
+        w2 = ops.conv_out_size(w, 2)
         y = ops.conv2d_fprop(x, self.w_stem, h, w, 3, (1, 2), self.act, None, self._buffer("stem", b, h, w2, 64, dev))
         w4 = w2 // 2
         cur = self._buffer("pool", b, h, w4, 64, dev)
@@ -95,7 +96,7 @@ class TensorCoreEncoder:
         feats = []
         for i, blk in enumerate(self.blocks):
             sh, sw = blk["stride"]
-            oh, ow, co = ch // sh, cw // sw, blk["cout"]
+            oh, ow, co = ops.conv_out_size(ch, sh), ops.conv_out_size(cw, sw), blk["cout"]
             t1 = ops.conv2d_fprop(cur, blk["w1"], ch, cw, 3, (sh, sw), self.act, None,
                                   self._buffer(f"b{i}a", b, oh, ow, co, dev))
             if blk["wd"] is not None:
@@ -151,7 +152,7 @@ class TensorCoreEncoder:
         st = {"B": b, "H": h, "W": w, "blocks": []}
         w_stem = next(it)
         st["x_in"] = ops.images_to_nhwc(image_1, image_2, 64)
-        w2 = w // 2
+        w2 = ops.conv_out_size(w, 2)
         st["y0"] = ops.conv2d_fprop(st["x_in"], _prep(w_stem, 64), h, w, 3, (1, 2), self.act, None,
                                     self._buffer("t_stem", b, h, w2, 64, dev))
         w4 = w2 // 2
@@ -165,7 +166,7 @@ class TensorCoreEncoder:
             w1, wc2 = next(it), next(it)
             wd = next(it) if blk["wd"] is not None else None
             sh, sw = blk["stride"]
-            oh, ow, co = ch // sh, cw // sw, blk["cout"]
+            oh, ow, co = ops.conv_out_size(ch, sh), ops.conv_out_size(cw, sw), blk["cout"]
             t1 = ops.conv2d_fprop(cur, _prep(w1), ch, cw, 3, (sh, sw), self.act, None,
                                   self._buffer(f"t{i}a", b, oh, ow, co, dev))
             if wd is not None:
@@ -209,10 +210,10 @@ class TensorCoreEncoder:
             g_wd = None
             if blk["wd"] is not None:
                 g_wd = ops.conv2d_wgrad(blk["x"], dz2, ch, cw, 1, (sh, sw))
-                up2 = ops.zero_upsample(dz2, oh, ow, (sh, sw), self._buffer(f"g{i}u2", b, ch, cw, cout, dev))
+                up2 = ops.zero_upsample(dz2, oh, ow, (sh, sw), self._buffer(f"g{i}u2", b, ch, cw, cout, dev), (ch, cw))
                 resid = ops.conv2d_fprop(up2, _prep_flip(blk["wd"]), ch, cw, 1, (1, 1), ops.ACT_NONE, None,
                                          self._buffer(f"g{i}d", b, ch, cw, cin, dev))
-                src = ops.zero_upsample(dz1, oh, ow, (sh, sw), self._buffer(f"g{i}u1", b, ch, cw, cout, dev))
+                src = ops.zero_upsample(dz1, oh, ow, (sh, sw), self._buffer(f"g{i}u1", b, ch, cw, cout, dev), (ch, cw))
             else:
                 resid, src = dz2, dz1
             if i > 0:     # the block input is the previous block's activation output: fold act' into the epilogue
@@ -223,7 +224,7 @@ class TensorCoreEncoder:
                                           self._buffer("g_pool", b, ch, cw, cin, dev))
             grads_rev.append((g_w1, g_w2, g_wd))
         h, w = st["H"], st["W"]
-        w2 = w // 2
+        w2 = ops.conv_out_size(w, 2)
         dz0 = self._buffer("g_stem", b, h, w2, 64, dev)
         ops._lib.check(L.delora_maxpool_w_bwd_nhwc_bf16(d_pool.data_ptr(), st["idx"].data_ptr(), st["y0"].data_ptr(), b, h,
                                                         w2, 64, act_id, dz0.data_ptr(), ops._stream()),

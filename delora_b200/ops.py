@@ -213,6 +213,22 @@ def icp_dense_fwd_bwd(src_grid, src_ngrid, transform, tgt_grid, tgt_ngrid, h, w,
     return losses, grad_t
 
 
+ICP_STATS = 256      # DELORA_ICP_STATS flag bit
+
+
+def icp_stats(reset=True):
+    """Search statistics of dense ICP calls made with `flags | ICP_STATS` (include/delora_b200.h)."""
+    import ctypes
+    buf = (ctypes.c_uint32 * 32)()
+    _lib.check(_lib.lib().delora_icp_stats(ctypes.cast(buf, ctypes.c_void_p), 1 if reset else 0), "delora_icp_stats")
+    v = list(buf)
+    names = ("0", "1-2", "3-5", "6-10", "11-20", "21-40", "41-63", "limit")
+    return {"warps": v[0], "steps": v[1], "cells_per_lane": v[2], "warps_block_search": v[3], "block_owners": v[4],
+            "blocks_bounded": v[5], "blocks_scanned": v[6], "max_blocks_scanned": v[7], "f64_rerank": v[8],
+            "max_blocks_bounded": v[9], "owners_over_256_blocks": v[10], "owners_without_candidate": v[11],
+            "warps_by_steps": dict(zip(names, v[16:24])), "cells_by_steps": dict(zip(names, v[24:32]))}
+
+
 def icp_point_grads(point_dir, normal_dir, n_src, losses, upstream):
     """-> grad_pts, grad_nrm [B,3,Ns] channels-first."""
     b, ns, _ = point_dir.shape
@@ -259,11 +275,16 @@ def padded_nhwc_zeros(b, h, w, c, device):
     return torch.zeros((b, h + 2, w + 2, c), dtype=torch.bfloat16, device=device)
 
 
+def conv_out_size(n, stride):
+    """Outputs of the encoder's 3x3/pad 1 and 1x1/pad 0 convolutions along one axis (any n, also odd)."""
+    return (n - 1) // stride + 1
+
+
 def conv2d_fprop(x, weight, hin, win, ksize, stride, act=ACT_NONE, residual=None, out=None, saved=None):
     """x [B,Hin+2,Win+2,Cin] bf16 padded NHWC, weight [Cout,k*k,Cin] bf16 -> y [B,Hout+2,Wout+2,Cout]."""
     b, _, _, cin = x.shape
     cout = weight.shape[0]
-    hout, wout = hin // stride[0], win // stride[1]
+    hout, wout = conv_out_size(hin, stride[0]), conv_out_size(win, stride[1])
     if out is None:
         out = padded_nhwc_zeros(b, hout, wout, cout, x.device)
     L = _lib.lib()
@@ -283,7 +304,7 @@ def conv2d_wgrad(x, dz, hin, win, ksize, stride, cin_true=None):
     b, _, _, cin = x.shape
     cout = dz.shape[3]
     cin_true = cin if cin_true is None else int(cin_true)
-    hout, wout = hin // stride[0], win // stride[1]
+    hout, wout = conv_out_size(hin, stride[0]), conv_out_size(win, stride[1])
     L = _lib.lib()
     n = int(L.delora_conv2d_wgrad_scratch_floats(b, hout, wout, cin, cout, ksize))
     key = (x.device.index, n)
@@ -298,13 +319,15 @@ def conv2d_wgrad(x, dz, hin, win, ksize, stride, cin_true=None):
     return dw
 
 
-def zero_upsample(x, h, w, stride, out=None):
-    """x [B,H+2,W+2,C] -> [B,H*sh+2,W*sw+2,C]: x at the strided positions, zero elsewhere."""
+def zero_upsample(x, h, w, stride, out=None, out_hw=None):
+    """x [B,H+2,W+2,C] -> [B,Hout+2,Wout+2,C]: x at the strided positions, zero elsewhere.  (Hout, Wout) is the
+    input size of the strided convolution whose output is H x W (default H*sh x W*sw)."""
     b, _, _, c = x.shape
+    ho, wo = out_hw if out_hw is not None else (h * stride[0], w * stride[1])
     if out is None:
-        out = torch.empty((b, h * stride[0] + 2, w * stride[1] + 2, c), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((b, ho + 2, wo + 2, c), dtype=torch.bfloat16, device=x.device)
     L = _lib.lib()
-    _lib.check(L.delora_zero_upsample_nhwc_bf16(_req(x, torch.bfloat16, "x"), b, h, w, c, stride[0], stride[1],
+    _lib.check(L.delora_zero_upsample_nhwc_bf16(_req(x, torch.bfloat16, "x"), b, h, w, c, stride[0], stride[1], ho, wo,
                                                 out.data_ptr(), _stream()), "delora_zero_upsample_nhwc_bf16")
     return out
 

@@ -38,7 +38,7 @@ class ScanPairPipeline:
         self.losses = torch.empty((self.B, ops.LOSS_ROW), dtype=f32, device=dev)
         self.grad_T = torch.empty((self.B, 12), dtype=f32, device=dev)
         self.icp_scratch = ops.icp_scratch(self.B, hw, dev)       # zeroed once; the kernels keep it armed
-        self.launches_per_step = 2 + 1 + 3   # scatter+resolve, normals(+grids), block_range+icp_dense+finalize
+        self.launches_per_step = 2 + 1 + 4   # scatter+resolve, normals(+grids), block_range+icp_dense+icp_dense_pending+finalize
 
     def load(self, scans_1, scans_2, transforms):
         """Host-side staging helper for tests: lists of [3,N_i] tensors + [B,4,4] transforms."""

@@ -39,6 +39,7 @@ typedef struct { float x, y, z, w; } delora_f4;
 #define DELORA_LOSS_PO2PL        2u   /* point_to_plane_loss                 */
 #define DELORA_LOSS_PL2PL        4u   /* plane_to_plane_loss                 */
 #define DELORA_NORMAL_LINEAR     8u   /* normal_loss: "linear" (default "squared") */
+#define DELORA_ICP_STATS       256u  /* diagnostic: count the work of the NN search (delora_icp_stats) */
 
 /* number of floats in one row of the `losses` output of delora_icp_fwd_bwd */
 #define DELORA_LOSS_ROW 8   /* [po2po, po2pl, pl2pl, M_pairs, M_po2po, 0, 0, 0] */
@@ -200,6 +201,15 @@ int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_f4* src_ngr
                              float lambda_po2pl, uint32_t flags, float* losses, float* grad_T,
                              float* scratch, void* stream);
 
+/* Diagnostic for delora_icp_dense_fwd_bwd calls made with DELORA_ICP_STATS in `flags`: copies the 32 device
+ * counters to the HOST array out32 (may be NULL) and optionally zeroes them.  [0] warps, [1] window-growing steps,
+ * [2] cells evaluated per lane (both summed per warp), [3] warps that entered the range-pruned block search,
+ * [4] lanes searched there, [5] blocks bounded, [6] blocks scanned, [7] max blocks scanned for one lane,
+ * [8] float64 tie re-rankings, [9] max blocks bounded for one lane, [10] lanes with > 256 blocks, [11] lanes that
+ * reached the block search without any candidate, [16..23] warps by number of steps {0, 1-2, 3-5, 6-10, 11-20, 21-40, 41-63, limit},
+ * [24..31] cells per lane summed over the warps of the same bucket.  Synchronises the device. */
+int delora_icp_stats(uint32_t* out32, int reset);
+
 /* Backward of ICPLosses.forward w.r.t. its two differentiable inputs, for callers that hand in
  * already-transformed clouds and let autograd continue (src/deploy/deployer.py:294-307 -> :341):
  * upstream [B,3] = d(total)/d(loss_po2po, loss_po2pl, loss_pl2pl);  losses = the row written by
@@ -232,12 +242,16 @@ int delora_conv2d_fprop_bf16(const void* x, const void* w, const void* residual,
 /* Weight gradient of the same convolution on tcgen05 (split-K over pixels, deterministic reduction):
  * x [B,Hin+2,Win+2,Cin] padded NHWC bf16 (the layer input), dz [B,Hout+2,Wout+2,Cout] padded NHWC bf16
  * (gradient w.r.t. the pre-activation output) -> dw [Cout, Cin_true, k, k] fp32 (torch layout; Cin_true <= Cin
- * for the channel-padded stem).  scratch: fp32 [delora_conv2d_wgrad_scratch_floats(...)].  Wout % 64 == 0. */
+ * for the channel-padded stem).  scratch: fp32 [delora_conv2d_wgrad_scratch_floats(...)].
+ * Any Hin, Win >= 1: Hout = (Hin-1)/stride_h + 1, Wout = (Win-1)/stride_w + 1; ragged tiles are zero-filled. */
 int64_t delora_conv2d_wgrad_scratch_floats(int B, int Hout, int Wout, int Cin, int Cout, int ksize);
 int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw, float* scratch, int B, int Hin, int Win,
                              int Cin, int Cin_true, int Cout, int ksize, int stride_h, int stride_w, void* stream);
-/* y[h*sh, w*sw] = x[h, w], zero elsewhere (padded NHWC bf16 in and out): input of the dgrad of strided convs */
-int delora_zero_upsample_nhwc_bf16(const void* x, int B, int H, int W, int C, int sh, int sw, void* y, void* stream);
+/* y[h*sh, w*sw] = x[h, w], zero elsewhere (padded NHWC bf16 in and out): input of the dgrad of strided convs.
+ * y is [B,Hout+2,Wout+2,C] with (Hout, Wout) the INPUT size of the strided convolution
+ * ((Hout-1)/sh+1 == H, (Wout-1)/sw+1 == W: 45 -> 23 -> 45 for the odd widths of 64x720 images). */
+int delora_zero_upsample_nhwc_bf16(const void* x, int B, int H, int W, int C, int sh, int sw, int Hout, int Wout,
+                                   void* y, void* stream);
 
 /* cat(image_1, image_2) ([B,4,H,W] fp32 each, src/models/model.py:98) -> [B,H+2,W+2,Cpad] bf16 padded NHWC */
 int delora_images_to_nhwc_bf16(const float* image_1, const float* image_2, int B, int H, int W, int Cpad,

@@ -45,21 +45,23 @@ for fn, name in ((t_proj, "projection"), (t_norm, "normals"), (t_icp, "icp_dense
 step = timeit(lambda: pipe.step(), "full step")
 print(f"sum of parts {tot*1e3:.1f} us; step {step*1e3:.1f} us -> {B/(step*1e-3):.0f} pairs/s")
 print("losses", pipe.losses[0].tolist())
-import ctypes
-dbg = (ctypes.c_uint * 8)()
-L.delora_debug_counters(None, 1); t_icp(); torch.cuda.synchronize(); L.delora_debug_counters(dbg, 1)
-print("phase2 stats: owners %d, blocks tested %d, blocks scanned %d, max scanned/owner %d, max rect blocks %d, warps in phase2 %d, max owners/warp %d" % tuple(dbg[:7]))
+import json
+def t_icp_stats():
+    _lib.check(L.delora_icp_dense_fwd_bwd(pipe.pts_grid.data_ptr() + B * hw * 16, pipe.nrm_grid.data_ptr() + B * hw * 16, pipe.transform.data_ptr(), pipe.pts_grid.data_ptr(), pipe.nrm_grid.data_ptr(), B, H, W, hf[0], hf[1], vf[0], vf[1], 1.0, 6 | ops.ICP_STATS, pipe.losses.data_ptr(), pipe.grad_T.data_ptr(), pipe.icp_scratch.data_ptr(), st), "i")
+def stats(tag):
+    ops.icp_stats(reset=True); t_icp_stats(); torch.cuda.synchronize()
+    print(tag, json.dumps(ops.icp_stats(reset=True)))
+stats("stats(predicted T)")
 # misaligned case: identity transform instead of the (nearly correct) predicted one -> NN distances ~0.5 m
-import torch as _t
-pipe.transform.copy_(_t.eye(4, device="cuda")[:3, :].reshape(1, 12).repeat(B, 1))
+import math
+saved_T = pipe.transform.clone()
+pipe.transform.copy_(torch.eye(4, device="cuda")[:3, :].reshape(1, 12).repeat(B, 1))
 timeit(t_icp, "icp_identityT")
+stats("stats(identity T)")
 print("losses(identity T)", pipe.losses[0].tolist())
-from delora_b200 import synthetic as _syn
-import math as _m
-tb = _t.from_numpy(_syn.transform_matrix(2.0, 1.0, 0.3, _m.radians(10.0), _m.radians(2.0), 0.0)).float().cuda()
+tb = torch.from_numpy(synthetic.transform_matrix(2.0, 1.0, 0.3, math.radians(10.0), math.radians(2.0), 0.0)).float().cuda()
 pipe.transform.copy_(tb[:3, :].reshape(1, 12).repeat(B, 1))
 timeit(t_icp, "icp_badT", iters=5)
-L.delora_debug_counters(None, 1); t_icp(); torch.cuda.synchronize(); L.delora_debug_counters(dbg, 1)
-print("badT phase2 stats: owners %d, blocks tested %d, blocks scanned %d, max scanned/owner %d, max rect blocks %d, warps in phase2 %d, max owners/warp %d" % tuple(dbg[:7]))
+stats("stats(bad T)")
 print("losses(bad T)", pipe.losses[0].tolist())
-
+pipe.transform.copy_(saved_T)

@@ -22,6 +22,15 @@ CASES = [  # B, Cin, Cout, H, W, k, stride, act, residual
     (2, 256, 512, 16, 128, 3, (2, 2), 2, False),
     (2, 256, 512, 16, 128, 1, (2, 2), 0, False),
     (1, 512, 512, 32, 64, 3, (1, 1), 2, True),
+    # KITTI 64x720 widths down the encoder (ragged tiles, odd sizes): 720 -> 360 -> 180 -> 90 -> 45 -> 23
+    (1, 64, 64, 64, 720, 3, (1, 2), 2, False),
+    (1, 64, 64, 64, 180, 3, (1, 1), 2, True),
+    (1, 64, 128, 64, 180, 3, (1, 2), 2, False),
+    (1, 128, 256, 64, 90, 1, (1, 2), 0, False),
+    (1, 256, 512, 64, 45, 3, (2, 2), 2, False),
+    (1, 256, 512, 64, 45, 1, (2, 2), 0, False),
+    (2, 512, 512, 32, 23, 3, (1, 1), 1, True),
+    (1, 64, 64, 6, 10, 3, (1, 1), 0, False),
 ]
 
 
@@ -31,7 +40,7 @@ def test_conv_fprop_matches_torch(b, cin, cout, h, w, k, stride, act, use_res, c
     g = torch.Generator(device=DEV).manual_seed(cin * 131 + cout + k)
     x = torch.randn(b, cin, h, w, device=DEV, generator=g) * 0.5
     wt = torch.randn(cout, cin, k, k, device=DEV, generator=g) / (cin * k * k) ** 0.5
-    ho, wo = h // stride[0], w // stride[1]
+    ho, wo = ops.conv_out_size(h, stride[0]), ops.conv_out_size(w, stride[1])
     res = torch.randn(b, cout, ho, wo, device=DEV, generator=g) * 0.5 if use_res else None
     wn = wt.permute(0, 2, 3, 1).reshape(cout, k * k, cin).contiguous().to(torch.bfloat16)
     y = ops.conv2d_fprop(to_padded_nhwc(x), wn, h, w, k, stride, act, to_padded_nhwc(res) if use_res else None)
@@ -59,11 +68,12 @@ def test_conv_rejects_unsupported_shapes(cuda_lib):
         ops.conv2d_fprop(x, w, 8, 128, 3, (1, 1))
 
 
-def test_tensor_core_encoder_matches_torch_model(cuda_lib):
+@pytest.mark.parametrize("h,w", [(64, 512), (64, 720), (16, 180)])
+def test_tensor_core_encoder_matches_torch_model(h, w, cuda_lib):
     from delora_b200 import ops, synthetic
     from delora_b200.models.model import OdometryModel
     from delora_b200.models.tc_encoder import TensorCoreEncoder
-    h, w, b = 64, 512, 2
+    b = 2
     cfg = synthetic.fov_config(h=h, w=w, device=DEV)
     cfg.update({"pre_feature_extraction": False, "resnet_outputs": 1000, "use_dropout": False, "layers": [2, 2, 2, 2],
                 "factor_fewer_resnet_channels": 1, "activation_fct": "tanh", "use_single_mlp_at_output": False})
@@ -94,7 +104,11 @@ def test_tensor_core_encoder_matches_torch_model(cuda_lib):
 @pytest.mark.parametrize("b,cin,cout,h,w,k,stride", [
     (2, 64, 64, 8, 128, 3, (1, 1)), (2, 64, 128, 16, 256, 3, (1, 2)), (2, 64, 128, 16, 256, 1, (1, 2)),
     (2, 256, 512, 16, 128, 3, (2, 2)), (2, 256, 512, 16, 128, 1, (2, 2)), (1, 512, 512, 32, 64, 3, (1, 1)),
-    (1, 512, 512, 8, 16, 3, (1, 1))])
+    (1, 512, 512, 8, 16, 3, (1, 1)),
+    # ragged / odd sizes (64x720 encoder): K tiles overhang the image, odd widths under stride 2
+    (1, 64, 64, 64, 180, 3, (1, 1)), (1, 64, 128, 64, 180, 3, (1, 2)), (1, 128, 256, 64, 90, 1, (1, 2)),
+    (1, 256, 512, 64, 45, 3, (2, 2)), (1, 256, 512, 64, 45, 1, (2, 2)), (2, 512, 512, 32, 23, 3, (1, 1)),
+    (1, 64, 64, 6, 10, 3, (1, 1))])
 def test_conv_dgrad_wgrad_match_autograd(b, cin, cout, h, w, k, stride, cuda_lib):
     """Backward of the convolution: wgrad kernel and dgrad (= fprop kernel on the zero-upsampled output
     gradient with the flipped filter) against torch autograd on bf16-rounded operands."""
@@ -103,7 +117,7 @@ def test_conv_dgrad_wgrad_match_autograd(b, cin, cout, h, w, k, stride, cuda_lib
     x = (torch.randn(b, cin, h, w, device=DEV, generator=g) * 0.5).to(torch.bfloat16).float().requires_grad_(True)
     wt = (torch.randn(cout, cin, k, k, device=DEV, generator=g) / (cin * k * k) ** 0.5).to(torch.bfloat16).float()
     wt.requires_grad_(True)
-    ho, wo = h // stride[0], w // stride[1]
+    ho, wo = ops.conv_out_size(h, stride[0]), ops.conv_out_size(w, stride[1])
     dz = (torch.randn(b, cout, ho, wo, device=DEV, generator=g) * 0.5).to(torch.bfloat16).float()
     if k == 3:
         y = F.conv2d(F.pad(x, (1, 1, 0, 0), mode="circular"), wt, stride=stride, padding=(1, 0))
@@ -115,17 +129,18 @@ def test_conv_dgrad_wgrad_match_autograd(b, cin, cout, h, w, k, stride, cuda_lib
     wf = wt.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k, cout).contiguous().to(torch.bfloat16)
     dzn = to_padded_nhwc(dz)
     if stride != (1, 1):
-        dzn = ops.zero_upsample(dzn, ho, wo, stride)
+        dzn = ops.zero_upsample(dzn, ho, wo, stride, out_hw=(h, w))
     dx = ops.nhwc_to_nchw(ops.conv2d_fprop(dzn, wf, h, w, k, (1, 1), ops.ACT_NONE), h, w)
     assert (dx - x.grad).abs().max().item() <= 8e-3 * x.grad.abs().max().item()        # bf16 output
 
 
-def test_encoder_training_path_gradients(cuda_lib):
+@pytest.mark.parametrize("h,w", [(64, 512), (64, 720)])
+def test_encoder_training_path_gradients(h, w, cuda_lib):
     """Full trunk forward + backward on tcgen05 (autograd Function) against torch fp32 autograd."""
     from delora_b200 import synthetic
     from delora_b200.models.model import OdometryModel
     from delora_b200.models.tc_encoder import TensorCoreEncoder
-    h, w, b = 64, 512, 2
+    b = 2
     cfg = synthetic.fov_config(h=h, w=w, device=DEV)
     cfg.update({"pre_feature_extraction": False, "resnet_outputs": 1000, "use_dropout": False, "layers": [2, 2, 2, 2],
                 "factor_fewer_resnet_channels": 1, "activation_fct": "tanh", "use_single_mlp_at_output": False})
