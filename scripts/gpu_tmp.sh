@@ -1,5 +1,2 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -x 2>&1 | tail -3
-for th in 256 128; do for mult in 4 8; do
-echo "== threads $th mult $mult"
-DELORA_ICP_PEND_THREADS=$th DELORA_ICP_PEND_MULT=$mult timeout 200 python scripts/gpu_explore.py 2>&1 | grep -E "^icp_dense|^icp_identityT|^icp_badT|^full step"
-done; done
+timeout 600 python -m pytest tests -q -m gpu -x -s 2>&1 | grep -E "normals_|passed|failed|Error|assert" | head -40
+timeout 200 python scripts/gpu_explore.py 2>&1 | grep -E "^projection|^normals|^icp_dense|^full step|^sum of"
