@@ -359,8 +359,11 @@ def run_ours(args):
                          "no flush kernels inside the timed region"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / K,
+                "h2d_gbs": h2d_bytes / (e2e_ms / K * 1e-3) / 1e9,
                 "how": "pinned host scans -> H2D on a copy stream (prefetch 1 step ahead) -> pipeline.step() -> "
-                       "D2H of losses[B,8] + grad_T[B,12]"},
+                       "D2H of losses[B,8] + grad_T[B,12]",
+                "bound": "host link: the raw fp32 scans (12 B/point) cross PCIe every step; when h2d_gbs is ~50 the "
+                         "copy, not the kernels, sets this number"},
         "gpu_launches": K * pipes[0].launches_per_step,
         "roofline": roofline, "kernels": kernels,
         "cpu_baseline": {"value": cpu_value, "unit": "pairs/s", "cores": cores, "kind": "port",

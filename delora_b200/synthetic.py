@@ -149,3 +149,22 @@ def edge_stress_cloud(h=16, w=180, vfov_deg=(-15.0, 15.0), r=7.5):
         pts.append((r * math.cos(el), 0.3 * math.cos(el), r * math.sin(el)))
     pts += [(5.0, 0.0, 0.0), (0.0, 5.0, 0.0), (3.0, 3.0, 0.0), (0.0, 0.0, 4.0), (-4.0, 0.0, 0.5), (0.0, 0.0, 0.0)]
     return torch.tensor(pts, dtype=torch.float32).t().contiguous()
+
+
+def kitti_bin_scan(index, w_raw=192, rings=16, vfov_deg=(-15.0, 15.0)):
+    """A synthetic scan in KITTI's velodyne .bin layout: [N, 4] float32 rows (x, y, z, reflectance)."""
+    scan_1, _, _, _ = make_pair(index, w_raw=w_raw, rings=rings, vfov_deg=vfov_deg)
+    g = torch.Generator().manual_seed(5000 + index)
+    refl = torch.rand(scan_1.shape[1], generator=g)
+    return torch.cat((scan_1, refl[None]), dim=0).t().contiguous().numpy().astype(np.float32)
+
+
+def preprocessing_config(data_path, preprocessed_path, h=16, w_pre=200, vfov_deg=(-15.0, 15.0), identifiers=(0,),
+                         device="cpu"):
+    """Config of the offline stage as bin/preprocess_data.py builds it (angles in radians)."""
+    cfg = fov_config(h=h, w=w_pre, vfov_deg=vfov_deg, device=device)
+    cfg["kitti"].update({"horizontal_cells_preprocessing": w_pre, "data_identifiers": list(identifiers),
+                         "data_path": str(data_path), "preprocessed_path": str(preprocessed_path),
+                         "dataset_type": "kitti"})
+    cfg["visualize_single_img_preprocessing"] = False
+    return cfg

@@ -203,5 +203,37 @@ def main():
     print("written to", GOLDEN)
 
 
+def preprocess_golden():
+    """The reference's offline stage end to end (src/preprocessing/preprocesser.py:50-103 through
+    src/data/kitti_scans.py): two synthetic KITTI .bin scans -> its own scans/ and normals/ .npy files."""
+    import tempfile
+    torch.set_num_threads(1)
+    pp = ref_harness.reference_preprocesser()
+    with tempfile.TemporaryDirectory() as tmp:
+        velo = os.path.join(tmp, "raw", "00", "velodyne")
+        os.makedirs(velo)
+        for k in range(2):
+            synthetic.kitti_bin_scan(60 + k).tofile(os.path.join(velo, format(k, "06d") + ".bin"))
+        cfg = synthetic.preprocessing_config(os.path.join(tmp, "raw"), os.path.join(tmp, "pre"))
+        pp.Preprocesser(config=cfg).preprocess_data()
+        out = {}
+        for k in range(2):
+            out[f"points_{k}"] = np.load(os.path.join(tmp, "pre", "00", "scans", format(k, "06d") + ".npy"))
+            out[f"normals_{k}"] = np.load(os.path.join(tmp, "pre", "00", "normals", format(k, "06d") + ".npy"))
+    np.savez_compressed(os.path.join(GOLDEN, "preprocess_16x200.npz"), **out)
+    # pin the oracle's composition (projection of the 4-channel cloud, normals, row-major lists)
+    from oracle import delora_oracle as orc
+    for k in range(2):
+        scan = torch.from_numpy(synthetic.kitti_bin_scan(60 + k)).t().contiguous()
+        img = orc.project_to_img(scan[None], 16, 200, cfg["horizontal_field_of_view"], cfg["kitti"]["vertical_field_of_view"])[0]
+        normals, _, points = orc.compute_normal_vectors(img)
+        print("preprocess scan", k, "points", np.array_equal(points.numpy(), out[f"points_{k}"]),
+              "normals", np.array_equal(normals.numpy(), out[f"normals_{k}"]), out[f"points_{k}"].shape)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--preprocess-only":
+        preprocess_golden()
+        sys.exit(0)
     main()
+    preprocess_golden()

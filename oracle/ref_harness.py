@@ -118,6 +118,29 @@ def install():
     _installed = True
 
 
+def reference_preprocesser():
+    """The reference's offline stage (`preprocessing.preprocesser.Preprocesser`, src/preprocessing/preprocesser.py),
+    imported unmodified.  Extra import-time stubs: `pykitti.utils.load_velo_scan` restated from pykitti 0.3.1
+    (`np.fromfile(file, dtype=np.float32).reshape((-1, 4))`; call site src/data/kitti_scans.py:44) and empty ROS
+    modules for `data.rosbag_scans`."""
+    install()
+    import numpy as np
+
+    def load_velo_scan(file):
+        return np.fromfile(file, dtype=np.float32).reshape((-1, 4))
+
+    utils = types.ModuleType("pykitti.utils")
+    utils.load_velo_scan = load_velo_scan
+    utils.yield_velo_scans = lambda files: (load_velo_scan(f) for f in files)
+    sys.modules["pykitti"].utils = utils
+    sys.modules["pykitti.utils"] = utils
+    for name in ("rosbag", "rospy", "ros_numpy", "sensor_msgs", "sensor_msgs.msg", "sensor_msgs.point_cloud2"):
+        if name not in sys.modules:
+            _stub(name)
+    import preprocessing.preprocesser
+    return preprocessing.preprocesser
+
+
 def reference_modules():
     """Returns the reference's hot-path modules, imported unmodified."""
     install()

@@ -193,3 +193,39 @@ def test_trainer_runs_and_checkpoints(tmp_path, cuda_lib):
     assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "loss", "parameters"}
     assert "resnet.conv1.weight" in ckpt["model_state_dict"]
     assert "fully_connected_rotation.1.weight" in ckpt["model_state_dict"]
+
+
+def test_offline_preprocesser_matches_reference_files(tmp_path, cuda_lib):
+    """`Preprocesser.preprocess_data()` on two synthetic KITTI .bin scans against the .npy files the REFERENCE's
+    own Preprocesser wrote for the same input (tests/golden/preprocess_16x200.npz): point lists bit-exact,
+    has-normal masks exact, normals to float tolerance; the output tree is what the training dataset reads."""
+    from delora_b200 import synthetic
+    from delora_b200.preprocessing.preprocesser import Preprocesser
+    z = np.load(os.path.join(GOLDEN, "preprocess_16x200.npz"))
+    velo = tmp_path / "raw" / "00" / "velodyne"
+    velo.mkdir(parents=True)
+    for k in range(2):
+        synthetic.kitti_bin_scan(60 + k).tofile(velo / (format(k, "06d") + ".bin"))
+    cfg = synthetic.preprocessing_config(tmp_path / "raw", tmp_path / "pre", device=DEV)
+    cfg["preprocessing_batch_size"] = 2
+    Preprocesser(config=cfg).preprocess_data()
+    for k in range(2):
+        pts = np.load(tmp_path / "pre" / "00" / "scans" / (format(k, "06d") + ".npy"))
+        nrm = np.load(tmp_path / "pre" / "00" / "normals" / (format(k, "06d") + ".npy"))
+        assert pts.dtype == np.float32 and nrm.dtype == np.float32 and pts.shape == nrm.shape
+        assert np.array_equal(pts, z[f"points_{k}"])
+        has_ref = (z[f"normals_{k}"] != 0).any(axis=1)
+        assert np.array_equal((nrm != 0).any(axis=1), has_ref)
+        err = np.linalg.norm(nrm - z[f"normals_{k}"], axis=1)[has_ref]
+        assert np.quantile(err, 0.99) < 2e-4 and (err > 1e-2).mean() < 2e-3
+    # per-scan entry point of the reference (same signature), single scan
+    pre = Preprocesser(config=cfg)
+    pre.config["dataset"] = "kitti"
+    from delora_b200.preprocessing.normal_computation import NormalsComputer
+    pre.normals_computer = NormalsComputer(config=cfg, dataset_name="kitti")
+    (tmp_path / "one" / "scans").mkdir(parents=True)
+    (tmp_path / "one" / "normals").mkdir(parents=True)
+    pre.scans_name, pre.normals_name = str(tmp_path / "one" / "scans"), str(tmp_path / "one" / "normals")
+    scan = torch.from_numpy(synthetic.kitti_bin_scan(60)).t().contiguous()[None]
+    pre.apply_preprocessing_step(scan=scan, index=7)
+    assert np.array_equal(np.load(tmp_path / "one" / "scans" / "000007.npy"), z["points_0"])

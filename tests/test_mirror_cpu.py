@@ -133,3 +133,20 @@ def test_gradient_allreduce_world_size_2_gloo(tmp_path):
     (model(x).pow(2).sum() / 2).backward()
     ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
     assert torch.allclose(r0["grad"], ref, rtol=1e-5, atol=1e-6)
+
+
+def test_kitti_bin_reader(tmp_path):
+    """`data.kitti_scans.KITTIPointCloudDataset`: sorted *.bin files -> [4, N] float32 (src/data/kitti_scans.py:35-50)."""
+    from delora_b200 import synthetic
+    from delora_b200.data.kitti_scans import KITTIPointCloudDataset
+    velo = tmp_path / "03" / "velodyne"
+    velo.mkdir(parents=True)
+    scans = [synthetic.kitti_bin_scan(70 + k) for k in range(3)]
+    for k in (2, 0, 1):
+        scans[k].tofile(velo / (format(k, "06d") + ".bin"))
+    ds = KITTIPointCloudDataset(base_dir=str(tmp_path), identifier=3, device="cpu")
+    assert len(ds) == 3 and ds.num_elements == 3
+    for k in range(3):
+        t = ds[k]
+        assert t.shape == (4, scans[k].shape[0]) and t.dtype == torch.float32
+        assert np.array_equal(t.t().numpy(), scans[k])

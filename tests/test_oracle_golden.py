@@ -144,3 +144,21 @@ def test_sleef_restatement_matches_torch_atan2():
     assert np.array_equal(mine(yy, xx).view(np.int32), ref.view(np.int32))
     nan = np.array([np.nan, 1.0] * 16, np.float32)
     assert np.isnan(mine(nan, nan[::-1].copy())).all()
+
+
+def test_offline_preprocessing_golden():
+    """The oracle's composition (4-channel projection -> normals -> row-major lists) against the files the
+    reference's own `Preprocesser.preprocess_data()` wrote for two synthetic KITTI .bin scans
+    (oracle/gen_golden.py:preprocess_golden)."""
+    from delora_b200 import synthetic
+    z = np.load(os.path.join(GOLDEN, "preprocess_16x200.npz"))
+    cfg = synthetic.preprocessing_config("unused", "unused")
+    for k in range(2):
+        scan = torch.from_numpy(synthetic.kitti_bin_scan(60 + k)).t().contiguous()
+        assert scan.shape[0] == 4
+        img = orc.project_to_img(scan[None], 16, 200, cfg["horizontal_field_of_view"],
+                                 cfg["kitti"]["vertical_field_of_view"])[0]
+        assert img.shape[1] == 5                                   # x, y, z, reflectance, range
+        normals, _, points = orc.compute_normal_vectors(img)
+        assert np.array_equal(points.numpy(), z[f"points_{k}"])
+        assert np.array_equal(normals.numpy(), z[f"normals_{k}"])
