@@ -103,17 +103,20 @@ def make_inputs(rank, n_sets):
     base = rank * PAIRS_PER_GPU * n_sets
     raw = [synthetic.make_pair(base + i, w_raw=W_RAW) for i in range(PAIRS_PER_GPU * n_sets)]
     n_max = max(max(p[0].shape[1], p[1].shape[1]) for p in raw)
+    from delora_b200.pipeline import ScanPairPipeline
+    layout = ScanPairPipeline.staging_layout(PAIRS_PER_GPU, 3, n_max)
     for s in range(n_sets):
-        pts = torch.zeros((2 * PAIRS_PER_GPU, 3, n_max), dtype=torch.float32).pin_memory()
-        cnt = torch.zeros((2 * PAIRS_PER_GPU,), dtype=torch.int32).pin_memory()
-        tr = torch.zeros((PAIRS_PER_GPU, 12), dtype=torch.float32).pin_memory()
+        # one pinned staging buffer per set, laid out like the pipeline's `inputs`: a step's scans, counts and
+        # transforms cross the host link as ONE copy
+        flat = torch.zeros((layout["bytes"],), dtype=torch.uint8).pin_memory()
+        pts, cnt, tr = ScanPairPipeline.input_views(flat, layout)
         for i in range(PAIRS_PER_GPU):
             s1, s2, _, t_pred = raw[s * PAIRS_PER_GPU + i]
             pts[i, :, :s1.shape[1]] = s1
             pts[PAIRS_PER_GPU + i, :, :s2.shape[1]] = s2
             cnt[i], cnt[PAIRS_PER_GPU + i] = s1.shape[1], s2.shape[1]
             tr[i] = t_pred[:3, :].reshape(12)
-        sets.append((pts, cnt, tr))
+        sets.append((pts, cnt, tr, flat))
     return sets, n_max, raw
 
 
@@ -195,10 +198,8 @@ def run_ours(args):
     ROTATE = max(1, args.rotate)
     sets, n_max, raw = make_inputs(rank, ROTATE)
     pipes = [ScanPairPipeline(PAIRS_PER_GPU, n_max, H, W, hf, vf, device=device) for _ in range(ROTATE)]
-    for p, (pts, cnt, tr) in zip(pipes, sets):
-        p.points.copy_(pts)
-        p.n_points.copy_(cnt)
-        p.transform.copy_(tr)
+    for p, (pts, cnt, tr, flat) in zip(pipes, sets):
+        p.inputs.copy_(flat)
     torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (`value`) + per-operator times -------------
@@ -236,10 +237,7 @@ def run_ours(args):
     def h2d(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(slot_free[slot])
-            pts, cnt, tr = sets[slot]
-            pipes[slot].points.copy_(pts, non_blocking=True)
-            pipes[slot].n_points.copy_(cnt, non_blocking=True)
-            pipes[slot].transform.copy_(tr, non_blocking=True)
+            pipes[slot].inputs.copy_(sets[slot][3], non_blocking=True)     # scans + counts + transforms, one copy
             h2d_done[slot].record(copy_stream)
 
     def e2e_loop(n):
@@ -268,7 +266,7 @@ def run_ours(args):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), world, device)
     clocks = sampler.stop()
     e2e_value = world * PAIRS_PER_GPU * K / (e2e_ms * 1e-3)
-    h2d_bytes = sum(t.numel() * t.element_size() for t in sets[0])
+    h2d_bytes = sets[0][3].numel()
     d2h_bytes = sum(t.numel() * t.element_size() for t in out_host[0])
     assert abs(out_host[0][0][0, 1].item() - losses0[1]) <= 1e-6 * abs(losses0[1]) + 1e-12
 

@@ -311,10 +311,10 @@ extern "C" int delora_icp_partial_rows(int src_stride) { return (src_stride + 31
 extern "C" int64_t delora_icp_scratch_floats(int B, int src_stride) {
     // partial rows + column sums + counters; then, for the dense path: the 4x16-cell range pyramid (2 floats per
     // block, at most src_stride/64 + H + W/16 + 1 <= src_stride/16 + 4096 blocks per pair) and the work list of
-    // its second kernel (4 counters, one int4 item per warp, one float4 of search state per source pixel)
+    // its second kernel (4 counters, int4 + done counter per warp, float4 search state + int result per source pixel)
     const int64_t rows = delora_icp_partial_rows(src_stride);
     return (int64_t)B * rows * DELORA_ICP_PARTIAL + (int64_t)B * DELORA_ICP_PARTIAL + B + 2 +
-           (int64_t)B * 2 * (src_stride / 16 + 4096) + 8 + 4 * (int64_t)B * rows + 4 * (int64_t)B * rows * 32;
+           (int64_t)B * 2 * (src_stride / 16 + 4096) + 8 + 5 * (int64_t)B * rows + 5 * (int64_t)B * rows * 32;
 }
 
 extern "C" int delora_icp_fwd_bwd(const delora_f4* src_pts4, const delora_f4* src_nrm4, const int32_t* n_src,

@@ -184,12 +184,14 @@ __device__ __forceinline__ SrcLane load_src_lane(const float4* __restrict__ src_
     return s;
 }
 
-// Work list of the second kernel (in `scratch`): one item per warp of icp_dense_kernel that gave up on
-// some of its lanes after `max_strips` window-growing steps.
+// Work list of the second kernel (in `scratch`).  An ITEM is a warp of icp_dense_kernel that gave up on some
+// of its lanes after `max_strips` window-growing steps; an ENTRY is one such lane.
 struct PendingList {
-    int* counters;          // [0] number of items, [1] CTAs of the second kernel that have finished; both 0 when idle
-    int4* items;            // (pair, warp in pair, mask of unfinished lanes, 0)
-    float4* state;          // [item][lane]: (m1, m2, bits(j1), 0) of the window search so far
+    int* counters;          // [0] items, [1] CTAs of the second kernel that have finished, [2] entries; 0 when idle
+    int4* items;            // (pair, warp in pair, mask of unfinished lanes, first entry)
+    int* item_done;         // entries of the item already searched (0 when idle)
+    float4* entries;        // (m1, m2, bits(j1), bits(item * 32 + lane)) of the window search so far
+    int* result;            // per entry: pixel id of the nearest neighbour
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -311,15 +313,19 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
             if (pending) atomicAdd(&g_dbg[3], 1u);
         }
         if (pending) {
-            // hand the unfinished lanes to kernel 2 (the order of the items is arbitrary, but every item owns
-            // its warp's partial row, so the sums stay deterministic)
-            int item = 0;
+            // hand the unfinished lanes to kernel 2 (items and entries land in arbitrary order, but every item
+            // owns its warp's partial row and adds to it in lane order, so the sums stay deterministic)
+            int item = 0, first = 0;
             if (lane == 0) {
                 item = atomicAdd(pend.counters, 1);
-                pend.items[item] = make_int4(b, warp_in_pair, (int)pending, 0);
+                first = atomicAdd(pend.counters + 2, __popc(pending));
+                pend.items[item] = make_int4(b, warp_in_pair, (int)pending, first);
             }
             item = __shfl_sync(0xffffffffu, item, 0);
-            pend.state[(size_t)item * 32 + lane] = make_float4(nn.m1, nn.m2, __int_as_float(nn.j1), 0.0f);
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if ((pending >> lane) & 1u)
+                pend.entries[first + __popc(pending & ((1u << lane) - 1u))] =
+                    make_float4(nn.m1, nn.m2, __int_as_float(nn.j1), __int_as_float(item * 32 + lane));
         }
         best_j = ((pending >> lane) & 1u) ? -1 : nn.j1;
         if (active && best_j >= 0 && nn.m2 <= nn.m1 * (1.0f + kNNBand)) {
@@ -441,12 +447,12 @@ __device__ __noinline__ int exact_rerank_warp(const float4* __restrict__ tg, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// Kernel 2: range-pruned block search for the lanes kernel 1 gave up on.  One CTA per item (= one warp of
-// kernel 1); its unfinished lanes ("owners") are dealt round-robin to the CTA's warps, and a whole warp
-// searches for ONE owner: 32 lanes bound 32 blocks of the certifying rectangle at a time and scan the
-// blocks that survive, 32 cells per step.  Warp 0 then adds the owners' loss / gradient terms to the partial
-// row kernel 1 wrote for that warp (fixed order: deterministic).  Persistent grid; the last CTA re-arms
-// the work list.
+// Kernel 2: range-pruned block search for the lanes kernel 1 gave up on.  One WARP per entry (= one source
+// point), no coupling between the warps of a CTA: the 32 lanes bound 32 blocks of the certifying rectangle at a
+// time and scan the blocks that survive, 2 cells per lane.  The warp that finishes the LAST entry of an item
+// (atomic count) adds the loss / gradient terms of all the item's entries to the partial row kernel 1 wrote
+// for that warp, in lane order (whichever warp does it, the arithmetic is the same: deterministic).
+// Persistent grid-stride over the entries; the last CTA re-arms the work list.
 constexpr int kPendThreads = 256;
 
 template <bool PO2PO, bool STATS>
@@ -456,105 +462,96 @@ icp_dense_pending_kernel(const float4* __restrict__ src_grid, const float4* __re
                          const float4* __restrict__ tgt_ngrid, const float2* __restrict__ blk_range, int nbh, int nbw,
                          GridParams g, uint32_t flags, float* __restrict__ partial_rows, int rows_per_pair,
                          PendingList pend) {
-    __shared__ int s_res[32];         // per owner lane: pixel id of its nearest neighbour (-1: none)
-    __shared__ float4 s_pos[32], s_uv[32];   // (sx, sy, sz, |s|), (u, v, |s_xy|, m1)
-    __shared__ int4 s_cell[32];              // (centre row, centre column, bits(m2), j1)
     const int H = g.H, W = g.W, HW = H * W;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int kWarps = (int)blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_cta = (int)blockDim.x >> 5;
+    const int gwarp = blockIdx.x * warps_per_cta + ((int)threadIdx.x >> 5), n_warps = gridDim.x * warps_per_cta;
     constexpr float kInf = 3.0e38f;
     constexpr float kSlack = 2e-3f;
-    const int n_items = *reinterpret_cast<volatile int*>(pend.counters);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int4 it = pend.items[item];
+    const int n_entries = *reinterpret_cast<volatile int*>(pend.counters + 2);
+    for (int e = gwarp; e < n_entries; e += n_warps) {
+        const float4 ent = __ldg(pend.entries + e);
+        const int code = __float_as_int(ent.w), item = code >> 5, owner = code & 31;
+        const int4 it = __ldg(pend.items + item);
         const int b = it.x, warp_in_pair = it.y;
         const unsigned pending = (unsigned)it.z;
         const float4* __restrict__ tg = tgt_grid + (size_t)b * HW;
-        const float4* __restrict__ tn = tgt_ngrid + (size_t)b * HW;
         const float2* __restrict__ blk = blk_range + (size_t)b * nbh * nbw;
-        // warp 0 rebuilds the 32 lanes of the item (transform, re-projection, search state) and shares them
-        // through shared memory; every warp then reads the lanes it searches for (broadcast reads, no shuffles)
-        SrcLane s;
-        if (warp == 0) {
-            s = load_src_lane(src_grid, src_ngrid, T, b, warp_in_pair * 32 + lane, HW, g);
-            const float4 st = pend.state[(size_t)item * 32 + lane];
-            s_pos[lane] = make_float4(s.sx, s.sy, s.sz, s.r);
-            s_uv[lane] = make_float4(s.us, s.vs, s.rxy, st.x);
-            s_cell[lane] = make_int4(s.rc, s.cc, __float_as_int(st.y), __float_as_int(st.z));
+        // every lane rebuilds the SAME source point (uniform addresses: broadcast loads)
+        const SrcLane o = load_src_lane(src_grid, src_ngrid, T, b, warp_in_pair * 32 + owner, HW, g);
+        const float osx = o.sx, osy = o.sy, osz = o.sz, orr = o.r, ous = o.us, ovs = o.vs, orxy = o.rxy;
+        NN2 nn;                                                          // the window-search result so far
+        nn.m1 = ent.x; nn.m2 = ent.y; nn.j1 = __float_as_int(ent.z);
+        float obest = nn.m1;                                             // running best d^2 (fp32), warp-uniform
+        const int obr = o.rc / kBlkH, obc = o.cc / kBlkW;
+        const float cos_es = orr > 0.0f ? orxy / orr : 1.0f;
+        NN2 loc;
+        loc.m1 = kInf; loc.m2 = kInf; loc.j1 = -1;
+        // Block rectangle that certifies the CURRENT best: grow it (warp-uniform scalar loops) until all
+        // four borders are at least d0 away; the best can only shrink while the rectangle is scanned, so
+        // one pass over its blocks is enough (no ring-by-ring dependency chain).
+        const float obest0 = obest;
+        const float d0 = (obest < kInf) ? sqrtf(obest) * (1.00001f / 0.9995f) : kInf;
+        int br_lo = obr, br_hi = obr, bc_lo = obc, bc_hi = obc;            // bc_* unwrapped
+        while (br_lo > 0 && border_bound(ovs - ((float)(br_lo * kBlkH) - 0.5f) - kSlack, g.dv_rad, orr) < d0) --br_lo;
+        while (br_hi < nbh - 1 &&
+               border_bound(((float)min(br_hi * kBlkH + kBlkH - 1, H - 1) + 0.5f) - ovs - kSlack, g.dv_rad, orr) < d0)
+            ++br_hi;
+        // (unwrapped block columns: W need not be a multiple of kBlkW, so the pixel span of block column
+        //  bc outside [0, nbw) is that of its wrapped twin shifted by +-W, not bc * kBlkW)
+        while (bc_hi - bc_lo + 1 < nbw &&
+               border_bound(ous - ((float)blk_u_lo(bc_lo, nbw, W) - 0.5f) - kSlack - (bc_lo <= 0 ? g.seam_px : 0.0f),
+                            g.du_rad, orxy) < d0) --bc_lo;
+        while (bc_hi - bc_lo + 1 < nbw &&
+               border_bound(((float)blk_u_hi(bc_hi, nbw, W) + 0.5f) - ous - kSlack - (bc_hi >= nbw - 1 ? g.seam_px : 0.0f),
+                            g.du_rad, orxy) < d0) ++bc_hi;
+        const int nbc = bc_hi - bc_lo + 1, nblk = (br_hi - br_lo + 1) * nbc;
+        const OwnerGeom og = {osx, osy, osz, ous, ovs, orr, cos_es};
+        const BlockRect rect = {br_lo, bc_lo, nbc, nblk};
+        double unused_d = 0.0;
+        int unused_j = 0;
+        const int dbg_scanned = block_pass<false>(tg, blk, g, nbw, og, rect, obest, loc, unused_d, unused_j);
+        if (STATS && lane == 0) {
+            atomicAdd(&g_dbg[4], 1u); atomicAdd(&g_dbg[5], (unsigned)nblk); atomicAdd(&g_dbg[6], (unsigned)dbg_scanned);
+            atomicMax(&g_dbg[7], (unsigned)dbg_scanned);
+            atomicMax(&g_dbg[9], (unsigned)nblk);
+            if (nblk > 256) atomicAdd(&g_dbg[10], 1u);
+            if (!(obest0 < kInf)) atomicAdd(&g_dbg[11], 1u);
         }
-        __syncthreads();
-        const int n_owners = __popc(pending);
-        for (int k = warp; k < n_owners; k += kWarps) {
-            const int owner = __fns(pending, 0, k + 1);                  // k-th unfinished lane
-            const float4 opos = s_pos[owner], ouv = s_uv[owner];
-            const int4 ocell = s_cell[owner];
-            const float osx = opos.x, osy = opos.y, osz = opos.z, orr = opos.w;
-            const float ous = ouv.x, ovs = ouv.y, orxy = ouv.z;
-            const int orc = ocell.x, occ = ocell.y;
-            NN2 nn;                                                      // the owner's window-search result
-            nn.m1 = ouv.w; nn.m2 = __int_as_float(ocell.z); nn.j1 = ocell.w;
-            float obest = nn.m1;                                         // running best d^2 (fp32), warp-uniform
-            const int obr = orc / kBlkH, obc = occ / kBlkW;
-            const float cos_es = orr > 0.0f ? orxy / orr : 1.0f;
-            NN2 loc;
-            loc.m1 = kInf; loc.m2 = kInf; loc.j1 = -1;
-            // Block rectangle that certifies the CURRENT best: grow it (warp-uniform scalar loops) until all
-            // four borders are at least d0 away; the best can only shrink while the rectangle is scanned, so
-            // one pass over its blocks is enough (no ring-by-ring dependency chain).
-            const float obest0 = obest;
-            const float d0 = (obest < kInf) ? sqrtf(obest) * (1.00001f / 0.9995f) : kInf;
-            int br_lo = obr, br_hi = obr, bc_lo = obc, bc_hi = obc;            // bc_* unwrapped
-            while (br_lo > 0 && border_bound(ovs - ((float)(br_lo * kBlkH) - 0.5f) - kSlack, g.dv_rad, orr) < d0) --br_lo;
-            while (br_hi < nbh - 1 &&
-                   border_bound(((float)min(br_hi * kBlkH + kBlkH - 1, H - 1) + 0.5f) - ovs - kSlack, g.dv_rad, orr) < d0)
-                ++br_hi;
-            // (unwrapped block columns: W need not be a multiple of kBlkW, so the pixel span of block column
-            //  bc outside [0, nbw) is that of its wrapped twin shifted by +-W, not bc * kBlkW)
-            while (bc_hi - bc_lo + 1 < nbw &&
-                   border_bound(ous - ((float)blk_u_lo(bc_lo, nbw, W) - 0.5f) - kSlack - (bc_lo <= 0 ? g.seam_px : 0.0f),
-                                g.du_rad, orxy) < d0) --bc_lo;
-            while (bc_hi - bc_lo + 1 < nbw &&
-                   border_bound(((float)blk_u_hi(bc_hi, nbw, W) + 0.5f) - ous - kSlack - (bc_hi >= nbw - 1 ? g.seam_px : 0.0f),
-                                g.du_rad, orxy) < d0) ++bc_hi;
-            const int nbc = bc_hi - bc_lo + 1, nblk = (br_hi - br_lo + 1) * nbc;
-            const OwnerGeom og = {osx, osy, osz, ous, ovs, orr, cos_es};
-            const BlockRect rect = {br_lo, bc_lo, nbc, nblk};
-            double unused_d = 0.0;
-            int unused_j = 0;
-            const int dbg_scanned = block_pass<false>(tg, blk, g, nbw, og, rect, obest, loc, unused_d, unused_j);
-            if (STATS && lane == 0) {
-                atomicAdd(&g_dbg[4], 1u); atomicAdd(&g_dbg[5], (unsigned)nblk); atomicAdd(&g_dbg[6], (unsigned)dbg_scanned);
-                atomicMax(&g_dbg[7], (unsigned)dbg_scanned);
-                atomicMax(&g_dbg[9], (unsigned)nblk);
-                if (nblk > 256) atomicAdd(&g_dbg[10], 1u);
-                if (!(obest0 < kInf)) atomicAdd(&g_dbg[11], 1u);
-            }
-            // merge the 32 partial results, then into the owner's own window-search result
+        // merge the 32 partial results, then into the window-search result
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float bm1 = __shfl_xor_sync(0xffffffffu, loc.m1, o), bm2 = __shfl_xor_sync(0xffffffffu, loc.m2, o);
-                const int bj = __shfl_xor_sync(0xffffffffu, loc.j1, o);
-                nn2_merge(loc, bm1, bm2, bj);
-            }
-            NN2 fin = nn;
-            nn2_merge(fin, loc.m1, loc.m2, loc.j1);
-            const float fm1 = __shfl_sync(0xffffffffu, fin.m1, 0), fm2 = __shfl_sync(0xffffffffu, fin.m2, 0);
-            int fj = __shfl_sync(0xffffffffu, fin.j1, 0);
-            if (fj >= 0 && fm2 <= fm1 * (1.0f + kNNBand)) {
-                // Two candidates inside the fp32 ambiguity band: float64 re-ranking (cKDTree's order) by the whole
-                // warp, over the blocks of the certified rectangle whose lower bound reaches into the band (every
-                // candidate of the band lies inside that rectangle: all cells outside it are farther than d0).
-                if (STATS && lane == 0) atomicAdd(&g_dbg[8], 1u);
-                const float thresh = fm1 * (1.0f + kNNBand);
-                const int ej = exact_rerank_warp(tg, blk, g, nbw, og, rect, thresh);
-                fj = (ej == 0x7fffffff) ? fj : ej;
-            }
-            if (lane == 0) s_res[owner] = fj;
+        for (int s2 = 16; s2 > 0; s2 >>= 1) {
+            const float bm1 = __shfl_xor_sync(0xffffffffu, loc.m1, s2), bm2 = __shfl_xor_sync(0xffffffffu, loc.m2, s2);
+            const int bj = __shfl_xor_sync(0xffffffffu, loc.j1, s2);
+            nn2_merge(loc, bm1, bm2, bj);
         }
-        __syncthreads();
-        if (warp == 0) {
+        NN2 fin = nn;
+        nn2_merge(fin, loc.m1, loc.m2, loc.j1);
+        const float fm1 = __shfl_sync(0xffffffffu, fin.m1, 0), fm2 = __shfl_sync(0xffffffffu, fin.m2, 0);
+        int fj = __shfl_sync(0xffffffffu, fin.j1, 0);
+        if (fj >= 0 && fm2 <= fm1 * (1.0f + kNNBand)) {
+            // Two candidates inside the fp32 ambiguity band: float64 re-ranking (cKDTree's order) by the whole
+            // warp, over the blocks of the certified rectangle whose lower bound reaches into the band (every
+            // candidate of the band lies inside that rectangle: all cells outside it are farther than d0).
+            if (STATS && lane == 0) atomicAdd(&g_dbg[8], 1u);
+            const float thresh = fm1 * (1.0f + kNNBand);
+            const int ej = exact_rerank_warp(tg, blk, g, nbw, og, rect, thresh);
+            fj = (ej == 0x7fffffff) ? fj : ej;
+        }
+        // publish the result; the warp that completes the item does the item's accumulation
+        int finisher = 0;
+        if (lane == 0) {
+            pend.result[e] = fj;
+            __threadfence();
+            finisher = (atomicAdd(pend.item_done + item, 1) == __popc(pending) - 1) ? 1 : 0;
+        }
+        finisher = __shfl_sync(0xffffffffu, finisher, 0);
+        if (finisher) {
+            __threadfence();
+            const float4* __restrict__ tn = tgt_ngrid + (size_t)b * HW;
+            const SrcLane s = load_src_lane(src_grid, src_ngrid, T, b, warp_in_pair * 32 + lane, HW, g);
             const bool mine = ((pending >> lane) & 1u) != 0u && s.active;
-            const int best_j = mine ? s_res[lane] : -1;
+            const int best_j = mine ? __ldcg(pend.result + it.w + __popc(pending & ((1u << lane) - 1u))) : -1;
             float acc[kIcpAcc];
 #pragma unroll
             for (int k = 0; k < kIcpAcc; ++k) acc[k] = 0.0f;
@@ -566,15 +563,17 @@ icp_dense_pending_kernel(const float4* __restrict__ src_grid, const float4* __re
             if (warp_in_pair < rows_per_pair)
                 add_warp_partials<(PO2PO ? kIcpAcc : 24)>(
                     acc, partial_rows + ((size_t)b * rows_per_pair + warp_in_pair) * DELORA_ICP_PARTIAL);
+            if (lane == 0) pend.item_done[item] = 0;                    // re-arm
         }
-        __syncthreads();                // s_res is reused by the next item
     }
     // re-arm the work list: the last CTA to get here has seen every other CTA finish
+    __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(pend.counters + 1, 1) == (int)gridDim.x - 1) {
             pend.counters[0] = 0;
             pend.counters[1] = 0;
+            pend.counters[2] = 0;
             __threadfence();
         }
     }
@@ -622,7 +621,9 @@ extern "C" int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_
     PendingList pend;
     pend.counters = reinterpret_cast<int*>(scratch + off);
     pend.items = reinterpret_cast<int4*>(scratch + off + 4);
-    pend.state = reinterpret_cast<float4*>(scratch + off + 4 + (size_t)4 * B * rows);
+    pend.entries = reinterpret_cast<float4*>(scratch + off + 4 + (size_t)4 * B * rows);
+    pend.item_done = reinterpret_cast<int*>(scratch + off + 4 + (size_t)4 * B * rows + (size_t)4 * B * rows * 32);
+    pend.result = pend.item_done + (size_t)B * rows;
     {
         dim3 gb((nbh * nbw * 32 + 255) / 256, B);
         block_range_kernel<<<gb, 256, 0, st>>>((const float4*)tgt_grid, H, W, nbh, nbw, blk);
@@ -634,7 +635,7 @@ extern "C" int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_
     if (const char* e = getenv("DELORA_ICP_PEND_MULT")) pend_mult = atoi(e);
     DELORA_CHECK_ARG(pend_threads >= 32 && pend_threads <= 256 && pend_threads % 32 == 0 && pend_mult >= 1,
                      "DELORA_ICP_PEND_THREADS / DELORA_ICP_PEND_MULT out of range");
-    const int pend_grid = (int)std::min<long long>((long long)B * rows, (long long)pend_mult * kNumSMs);
+    const int pend_grid = (int)std::min<long long>(((long long)B * rows * 32 + 7) / 8, (long long)pend_mult * kNumSMs);
 #define DELORA_LAUNCH_DENSE(PO2PO, STATS)                                                                           \
     do {                                                                                                            \
         icp_dense_kernel<PO2PO, STATS><<<grid, kDenseThreads, 0, st>>>(                                             \

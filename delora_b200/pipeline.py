@@ -26,19 +26,41 @@ class ScanPairPipeline:
             raise RuntimeError("delora_b200 runs on CUDA devices only (no CPU fallback)")
         b2, hw, dev = 2 * self.B, self.H * self.W, self.device
         f32, i32 = torch.float32, torch.int32
-        self.points = torch.zeros((b2, self.C, self.N), dtype=f32, device=dev)     # [scan_1 x B | scan_2 x B]
-        self.n_points = torch.zeros((b2,), dtype=i32, device=dev)
+        # the three inputs of a step live in ONE allocation (`inputs`, raw bytes) so that a host caller can ship
+        # them with a single pinned-memory copy: [points | n_points | transform], each 256-byte aligned
+        self.input_layout = self.staging_layout(self.B, self.C, self.N)
+        self.inputs = torch.zeros((self.input_layout["bytes"],), dtype=torch.uint8, device=dev)
+        self.points, self.n_points, self.transform = self.input_views(self.inputs, self.input_layout)
         self.keys = torch.full((b2, hw), -1, dtype=torch.int64, device=dev)
         self.image = torch.empty((b2, self.C + 1, self.H, self.W), dtype=f32, device=dev)
         self.index_map = torch.empty((b2, self.H, self.W), dtype=i32, device=dev)
         # dense float4 grids written by the normals kernel: (x,y,z,pixel id) / (nx,ny,nz,has_normal)
         self.pts_grid = torch.empty((b2, hw, 4), dtype=f32, device=dev)
         self.nrm_grid = torch.empty((b2, hw, 4), dtype=f32, device=dev)
-        self.transform = torch.zeros((self.B, 12), dtype=f32, device=dev)
         self.losses = torch.empty((self.B, ops.LOSS_ROW), dtype=f32, device=dev)
         self.grad_T = torch.empty((self.B, 12), dtype=f32, device=dev)
         self.icp_scratch = ops.icp_scratch(self.B, hw, dev)       # zeroed once; the kernels keep it armed
         self.launches_per_step = 2 + 1 + 4   # scatter+resolve, normals(+grids), block_range+icp_dense+icp_dense_pending+finalize
+
+    @staticmethod
+    def staging_layout(batch, channels, n_max):
+        """Byte offsets of (points [2B,C,N] f32, n_points [2B] i32, transform [B,12] f32) inside `inputs`."""
+        def up(x):
+            return (x + 255) // 256 * 256
+        p_bytes = 2 * batch * channels * n_max * 4
+        n_off = up(p_bytes)
+        t_off = up(n_off + 2 * batch * 4)
+        return {"B": batch, "C": channels, "N": n_max, "n_points": n_off, "transform": t_off,
+                "bytes": up(t_off + batch * 12 * 4)}
+
+    @staticmethod
+    def input_views(buf, layout):
+        """Typed views (points, n_points, transform) of a flat uint8 buffer (device `inputs` or a pinned host twin)."""
+        b, c, n = layout["B"], layout["C"], layout["N"]
+        points = buf[:2 * b * c * n * 4].view(torch.float32).view(2 * b, c, n)       # [scan_1 x B | scan_2 x B]
+        n_points = buf[layout["n_points"]:layout["n_points"] + 2 * b * 4].view(torch.int32)
+        transform = buf[layout["transform"]:layout["transform"] + b * 48].view(torch.float32).view(b, 12)
+        return points, n_points, transform
 
     def load(self, scans_1, scans_2, transforms):
         """Host-side staging helper for tests: lists of [3,N_i] tensors + [B,4,4] transforms."""
