@@ -308,6 +308,48 @@ def run_ours(args):
         except Exception as e:                      # informational leg: never takes the headline down
             train = {"error": repr(e)[:300]}
 
+    # ---------------- streaming inference (BASELINE configs[4]), informational, rank 0 only ----------------
+    stream = None
+    if args.stream_frames > 0 and rank == 0:
+        try:
+            from delora_b200.deploy.stream import OdometryStream
+            from delora_b200.models.model import OdometryModel
+            scfg = synthetic.fov_config(h=H, w=W, device=device)
+            scfg.update({"pre_feature_extraction": False, "resnet_outputs": 1000, "use_dropout": False,
+                         "layers": [2, 2, 2, 2], "factor_fewer_resnet_channels": 1, "activation_fct": "tanh",
+                         "use_single_mlp_at_output": False, "use_tensor_core_encoder": True})
+            torch.manual_seed(4321)
+            smodel = OdometryModel(scfg).to(device).eval()
+            frames = [raw[i % len(raw)][i // len(raw) % 2] for i in range(min(len(raw) * 2, 32))]
+            lat = {}
+            import gc
+            gc.collect()
+            gc.freeze()            # keep the collector away from the (large, static) bench heap while frames are timed
+            for graph in (True, False):
+                st = OdometryStream(smodel, scfg, "kitti", n_max, use_cuda_graph=graph)
+                for i in range(8):                                   # first frame, capture, warm-up
+                    st.push(frames[i % len(frames)])
+                ts_ = []
+                for i in range(args.stream_frames):
+                    t0 = time.perf_counter()
+                    st.push(frames[i % len(frames)])
+                    ts_.append((time.perf_counter() - t0) * 1e3)
+                worst = max(range(len(ts_)), key=lambda j: ts_[j])
+                srt = sorted(ts_)
+                lat[graph] = (srt[len(srt) // 2], srt[min(len(srt) - 1, int(0.99 * len(srt)))], srt[-1], worst)
+                del st
+            stream = {"workload": f"inference stream, batch 1, 64x{W}, N~{n_max}: pinned host scan -> H2D -> 1 projection "
+                                  "(previous range image cached) + tcgen05 encoder forward + heads + quaternion->T "
+                                  "-> D2H of T, host-timed per frame (perf_counter around push(), includes the sync)",
+                      "frames": args.stream_frames, "ms_per_frame_p50": lat[True][0], "ms_per_frame_p99": lat[True][1],
+                      "frames_per_s": 1e3 / lat[True][0], "cuda_graph": True,
+                      "ms_per_frame_max": lat[True][2], "slowest_frame_index": lat[True][3],
+                      "eager_ms_per_frame_p50": lat[False][0], "eager_ms_per_frame_p99": lat[False][1]}
+            gc.unfreeze()
+            del smodel
+        except Exception as e:                      # informational leg: never takes the headline down
+            stream = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -369,6 +411,7 @@ def run_ours(args):
                                    f"(torch {torch.__version__} CPU + scipy cKDTree), {cores} of {os.cpu_count()} host threads "
                                    f"(best of a sweep), {cpu_dt:.1f} s"},
         "train_step": train,
+        "inference_stream": stream,
         "clocks": clocks, "wall_s_timed_region": t_wall,
         "check": {"loss_po2pl": losses0[1], "loss_pl2pl": losses0[2], "pairs": losses0[3],
                   "cpu_loss_po2pl": out["loss_po2pl"], "cpu_loss_pl2pl": out["loss_pl2pl"]},
@@ -385,6 +428,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-pairs", type=int, default=3, help="pairs timed for the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--stream-frames", type=int, default=200,
+                    help="frames of the informational streaming-inference leg (0 = skip)")
     ap.add_argument("--train-steps", type=int, default=5, help="steps of the informational full-training-step leg (0 = skip)")
     ap.add_argument("--train-batch", type=int, default=16)
     ap.add_argument("--rotate", type=int, default=ROTATE, help="rotating input sets (1 only for profiling runs)")

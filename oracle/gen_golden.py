@@ -231,9 +231,31 @@ def preprocess_golden():
               "normals", np.array_equal(normals.numpy(), out[f"normals_{k}"]), out[f"points_{k}"].shape)
 
 
+def poses_golden():
+    """Pose chaining (src/utility/poses.py:11-58) of 40 slightly non-orthonormal relative transforms."""
+    ref_harness.install()
+    import utility.poses as ref_poses
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(11)
+    rel = []
+    for _ in range(40):
+        t = np.eye(4)[None].copy()
+        t[0, :3, :3] = Rotation.from_euler("zyx", rng.normal(0, [0.03, 0.005, 0.005])).as_matrix()
+        t[0, :3, :3] += rng.normal(0, 1e-7, (3, 3))          # slightly off SO(3), as a network output is
+        t[0, :3, 3] = rng.normal([1.0, 0, 0], [0.2, 0.05, 0.02])
+        rel.append(t.astype(np.float32))
+    out = ref_poses.compute_poses([t.copy() for t in rel])
+    np.savez_compressed(os.path.join(GOLDEN, "poses.npz"), relative=np.stack(rel), poses=out)
+    print("poses", out.shape)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--poses-only":
+        poses_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--preprocess-only":
         preprocess_golden()
         sys.exit(0)
     main()
     preprocess_golden()
+    poses_golden()

@@ -229,3 +229,70 @@ def test_offline_preprocesser_matches_reference_files(tmp_path, cuda_lib):
     scan = torch.from_numpy(synthetic.kitti_bin_scan(60)).t().contiguous()[None]
     pre.apply_preprocessing_step(scan=scan, index=7)
     assert np.array_equal(np.load(tmp_path / "one" / "scans" / "000007.npy"), z["points_0"])
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_odometry_stream_one_projection_per_frame(use_graph, cuda_lib):
+    """`deploy.stream.OdometryStream`: frame k costs one projection (frame k-1's image is cached) + encoder +
+    quaternion->T, optionally replayed as one CUDA graph; the relative transforms must equal the pairwise
+    inference path (both projections recomputed, eager launches) bit for bit."""
+    from delora_b200 import ops, synthetic
+    from delora_b200.deploy.stream import OdometryStream
+    from delora_b200.models.model import OdometryModel
+    from delora_b200.models.model_parts import GeometryHandler
+    h, w = 64, 512
+    cfg = synthetic.fov_config(h=h, w=w, device=DEV)
+    cfg.update({"pre_feature_extraction": False, "resnet_outputs": 1000, "use_dropout": False, "layers": [2, 2, 2, 2],
+                "factor_fewer_resnet_channels": 1, "activation_fct": "tanh", "use_single_mlp_at_output": False,
+                "use_tensor_core_encoder": True})
+    torch.manual_seed(3)
+    model = OdometryModel(cfg).to(DEV).eval()
+    frames = []
+    for i in range(3):
+        s1, s2, _, _ = synthetic.make_pair(80 + i, w_raw=512)
+        frames += [s1, s2]
+    n_max = max(f.shape[1] for f in frames)
+    stream = OdometryStream(model, cfg, "kitti", n_max, use_cuda_graph=use_graph)
+    got = [stream.push(f) for f in frames]
+    assert got[0] is None and all(g.shape == (1, 4, 4) for g in got[1:])
+    hf, vf = cfg["horizontal_field_of_view"], cfg["kitti"]["vertical_field_of_view"]
+
+    def image_of(f):
+        pts = torch.zeros((1, 3, n_max), device=DEV)
+        pts[0, :, :f.shape[1]] = f.to(DEV)
+        return ops.project(pts, torch.tensor([f.shape[1]], dtype=torch.int32, device=DEV), h, w, hf, vf)[0]
+
+    for k in range(1, len(frames)):
+        with torch.no_grad():
+            t, q = model(image_1=image_of(frames[k - 1]), image_2=image_of(frames[k]))
+            ref = GeometryHandler.get_transformation_matrix_quaternion(translation=t, quaternion=q, device=DEV)
+        assert np.array_equal(got[k], ref.cpu().numpy()), k
+    poses = stream.poses()
+    assert poses.shape == (len(frames), 4, 4) and np.allclose(poses[0], np.eye(4))
+
+
+def test_tester_inference_collects_transforms(tmp_path, cuda_lib):
+    from delora_b200.deploy.tester import Tester
+    from delora_b200.models.model import OdometryModel
+    write_preprocessed(tmp_path, n_scans=4)
+    cfg = tiny_training_config(tmp_path, batch_size=1)
+    torch.manual_seed(0)
+    ckpt = tmp_path / "model.pth"
+    torch.save({"model_state_dict": OdometryModel(cfg).state_dict()}, ckpt)
+    cfg.update({"checkpoint": str(ckpt), "inference_only": True, "mode": "testing"})
+    tester = Tester(config=cfg)
+    tester.test()
+    rel = tester.computed_transformations_datasets[0][0]
+    assert len(rel) == len(tester.dataset) == 3 and all(t.shape == (1, 4, 4) for t in rel)
+    # the same pairs through Deployer.step directly
+    d = tester.dataset[1]
+    for k in d:
+        if hasattr(d[k], "to"):
+            d[k] = d[k].to(DEV)
+    with torch.no_grad():
+        direct = tester.step(preprocessed_dicts=[d])
+    assert np.array_equal(direct.cpu().numpy(), rel[1])
+    assert tester.poses().shape == (4, 4, 4)
+    cfg["checkpoint"] = None
+    with pytest.raises(Exception, match="No checkpoint"):
+        Tester(config=cfg)

@@ -150,3 +150,15 @@ def test_kitti_bin_reader(tmp_path):
         t = ds[k]
         assert t.shape == (4, scans[k].shape[0]) and t.dtype == torch.float32
         assert np.array_equal(t.t().numpy(), scans[k])
+
+
+def test_compute_poses_golden(tmp_path):
+    """`utility.poses.compute_poses` against the reference's output (tests/golden/poses.npz) + the KITTI pose file."""
+    from delora_b200.utility import poses
+    z = np.load(os.path.join(GOLDEN, "poses.npz"))
+    out = poses.compute_poses([t.copy() for t in z["relative"]])
+    assert out.shape == z["poses"].shape == (41, 4, 4)
+    assert np.abs(out - z["poses"]).max() < 1e-12
+    poses.write_poses_to_text_file(str(tmp_path / "poses.txt"), out)
+    rows = np.loadtxt(tmp_path / "poses.txt")
+    assert rows.shape == (41, 12) and np.allclose(rows, out.reshape(41, 16)[:, :12])
