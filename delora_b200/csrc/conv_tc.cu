@@ -545,32 +545,49 @@ zero_upsample_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, i
 __global__ void __launch_bounds__(256)
 maxpool_idx_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, __nv_bfloat16* __restrict__ y,
                         uint8_t* __restrict__ idx) {
-    const int Wout = W / 2;
-    const size_t total = (size_t)B * H * Wout * C;
+    // one thread = 8 channels of one output pixel: 16-byte loads / stores, 8-byte argmax store
+    const int Wout = W / 2, groups = C / 8;
+    const size_t total = (size_t)B * H * Wout * groups;
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= total) return;
-    const int c = (int)(i % C);
-    size_t r = i / C;
+    const int grp = (int)(i % groups);
+    size_t r = i / groups;
     const int wo = (int)(r % Wout); r /= Wout;
     const int ho = (int)(r % H);
     const int b = (int)(r / H);
     const int Wp = W + 2, Hp = H + 2, Wpo = Wout + 2;
-    float m = -INFINITY;
-    int arg = 4;
+    float m[8];
+    int arg[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { m[e] = -INFINITY; arg[e] = 4; }
+#pragma unroll
     for (int dr = 0; dr < 3; ++dr) {
         const int h = ho + dr - 1;
         if (h < 0 || h >= H) continue;
+#pragma unroll
         for (int dq = 0; dq < 3; ++dq) {
-            const float v = __bfloat162float(x[(((size_t)b * Hp + h + 1) * Wp + 2 * wo + dq) * C + c]);
-            if (v > m) { m = v; arg = dr * 3 + dq; }
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * Hp + h + 1) * Wp + 2 * wo + dq) * C) + grp);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h2[e]);
+                if (f.x > m[2 * e]) { m[2 * e] = f.x; arg[2 * e] = dr * 3 + dq; }
+                if (f.y > m[2 * e + 1]) { m[2 * e + 1] = f.y; arg[2 * e + 1] = dr * 3 + dq; }
+            }
         }
     }
-    const __nv_bfloat16 o = __float2bfloat16_rn(m);
+    __nv_bfloat162 o2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(m[2 * e], m[2 * e + 1]);
+    const uint4 out = *reinterpret_cast<uint4*>(o2);
     const size_t pix = ((size_t)b * Hp + ho + 1) * Wpo + wo + 1;
-    y[pix * C + c] = o;
-    if (wo == 0) y[(pix + Wout) * C + c] = o;
-    if (wo == Wout - 1) y[(pix - Wout) * C + c] = o;
-    idx[i] = (uint8_t)arg;
+    reinterpret_cast<uint4*>(y + pix * C)[grp] = out;
+    if (wo == 0) reinterpret_cast<uint4*>(y + (pix + Wout) * C)[grp] = out;
+    if (wo == Wout - 1) reinterpret_cast<uint4*>(y + (pix - Wout) * C)[grp] = out;
+    uint2 packed;
+    packed.x = (unsigned)arg[0] | ((unsigned)arg[1] << 8) | ((unsigned)arg[2] << 16) | ((unsigned)arg[3] << 24);
+    packed.y = (unsigned)arg[4] | ((unsigned)arg[5] << 8) | ((unsigned)arg[6] << 16) | ((unsigned)arg[7] << 24);
+    reinterpret_cast<uint2*>(idx + ((((size_t)b * H + ho) * Wout + wo) * C))[grp] = packed;
 }
 
 // Backward of that pool fused with the derivative of the activation that produced its input:
@@ -581,17 +598,20 @@ __global__ void __launch_bounds__(256)
 maxpool_bwd_act_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                        const __nv_bfloat16* __restrict__ a, int B, int H, int W, int C, int act,
                        __nv_bfloat16* __restrict__ dz) {
-    const int Wout = W / 2;
-    const size_t total = (size_t)B * H * W * C;
+    // one thread = 8 channels of one input pixel (16-byte accesses)
+    const int Wout = W / 2, groups = C / 8;
+    const size_t total = (size_t)B * H * W * groups;
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= total) return;
-    const int c = (int)(i % C);
-    size_t r = i / C;
+    const int grp = (int)(i % groups);
+    size_t r = i / groups;
     const int w = (int)(r % W); r /= W;
     const int h = (int)(r % H);
     const int b = (int)(r / H);
     const int Wp = W + 2, Hp = H + 2, Wpo = Wout + 2;
-    float g = 0.0f;
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = 0.0f;
     // padded columns that hold this input column: w+1 always; 0 if w == W-1; W+1 if w == 0
     for (int alias = 0; alias < 3; ++alias) {
         int wp;
@@ -606,19 +626,38 @@ maxpool_bwd_act_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __re
             for (int dr = 0; dr < 3; ++dr) {             // window row offset: h = ho + dr - 1
                 const int ho = h - dr + 1;
                 if (ho < 0 || ho >= H) continue;
-                const size_t o = (((size_t)b * H + ho) * Wout + wo) * C + c;
-                if (idx[o] == dr * 3 + dq)
-                    g += __bfloat162float(dy[(((size_t)b * Hp + ho + 1) * Wpo + wo + 1) * C + c]);
+                const uint2 am = __ldg(reinterpret_cast<const uint2*>(idx + (((size_t)b * H + ho) * Wout + wo) * C) + grp);
+                const unsigned want = (unsigned)(dr * 3 + dq) * 0x01010101u;
+                const unsigned eq_lo = am.x ^ want, eq_hi = am.y ^ want;      // a zero byte = this window's argmax is (h, w)
+                if ((((eq_lo - 0x01010101u) & ~eq_lo) | ((eq_hi - 0x01010101u) & ~eq_hi)) & 0x80808080u) {
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(dy + (((size_t)b * Hp + ho + 1) * Wpo + wo + 1) * C) + grp);
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(h2[e]);
+                        const unsigned word = (e < 2) ? eq_lo : eq_hi;
+                        if (((word >> (16 * (e & 1))) & 0xffu) == 0u) g[2 * e] += f.x;
+                        if (((word >> (16 * (e & 1) + 8)) & 0xffu) == 0u) g[2 * e + 1] += f.y;
+                    }
+                }
             }
         }
     }
-    const float av = __bfloat162float(a[(((size_t)b * Hp + h + 1) * Wp + w + 1) * C + c]);
-    const float d = (act == 2) ? fmaf(-av, av, 1.0f) : (act == 1 ? (av > 0.0f ? 1.0f : 0.0f) : 1.0f);
-    const __nv_bfloat16 o = __float2bfloat16_rn(g * d);
+    const uint4 araw = __ldg(reinterpret_cast<const uint4*>(a + (((size_t)b * Hp + h + 1) * Wp + w + 1) * C) + grp);
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&araw);
+    __nv_bfloat162 o2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 av = __bfloat1622float2(a2[e]);
+        const float d0 = (act == 2) ? fmaf(-av.x, av.x, 1.0f) : (act == 1 ? (av.x > 0.0f ? 1.0f : 0.0f) : 1.0f);
+        const float d1 = (act == 2) ? fmaf(-av.y, av.y, 1.0f) : (act == 1 ? (av.y > 0.0f ? 1.0f : 0.0f) : 1.0f);
+        o2[e] = __floats2bfloat162_rn(g[2 * e] * d0, g[2 * e + 1] * d1);
+    }
+    const uint4 out = *reinterpret_cast<uint4*>(o2);
     const size_t pix = ((size_t)b * Hp + h + 1) * Wp + w + 1;
-    dz[pix * C + c] = o;
-    if (w == 0) dz[(pix + W) * C + c] = o;
-    if (w == W - 1) dz[(pix - W) * C + c] = o;
+    reinterpret_cast<uint4*>(dz + pix * C)[grp] = out;
+    if (w == 0) reinterpret_cast<uint4*>(dz + (pix + W) * C)[grp] = out;
+    if (w == W - 1) reinterpret_cast<uint4*>(dz + (pix - W) * C)[grp] = out;
 }
 
 // Backward of AdaptiveAvgPool2d((1,1)) fused with the derivative of the last block's activation:
@@ -890,8 +929,8 @@ extern "C" int delora_zero_upsample_nhwc_bf16(const void* x, int B, int H, int W
 }
 
 extern "C" int delora_maxpool_w_idx_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* idx, void* stream) {
-    DELORA_CHECK_ARG(x && y && idx && W % 2 == 0, "delora_maxpool_w_idx_nhwc_bf16: bad argument");
-    const size_t total = (size_t)B * H * (W / 2) * C;
+    DELORA_CHECK_ARG(x && y && idx && W % 2 == 0 && C % 8 == 0, "delora_maxpool_w_idx_nhwc_bf16: bad argument");
+    const size_t total = (size_t)B * H * (W / 2) * (C / 8);
     maxpool_idx_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, B, H, W, C, (__nv_bfloat16*)y, (uint8_t*)idx);
     DELORA_CHECK_LAUNCH("maxpool_idx_nhwc_kernel");
@@ -900,8 +939,8 @@ extern "C" int delora_maxpool_w_idx_nhwc_bf16(const void* x, int B, int H, int W
 
 extern "C" int delora_maxpool_w_bwd_nhwc_bf16(const void* dy, const void* idx, const void* a, int B, int H, int W, int C,
                                               int act, void* dz, void* stream) {
-    DELORA_CHECK_ARG(dy && idx && a && dz && W % 2 == 0, "delora_maxpool_w_bwd_nhwc_bf16: bad argument");
-    const size_t total = (size_t)B * H * W * C;
+    DELORA_CHECK_ARG(dy && idx && a && dz && W % 2 == 0 && C % 8 == 0, "delora_maxpool_w_bwd_nhwc_bf16: bad argument");
+    const size_t total = (size_t)B * H * W * (C / 8);
     maxpool_bwd_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dy, (const uint8_t*)idx, (const __nv_bfloat16*)a, B, H, W, C, act, (__nv_bfloat16*)dz);
     DELORA_CHECK_LAUNCH("maxpool_bwd_act_kernel");
