@@ -367,12 +367,24 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(dom)
+            tdoc = json.load(f)
+        traffic = tdoc.get(dom)
+        # the three operators are instruction-issue bound, not HBM bound: next to the HBM
+        # fraction report how full the issue slots are -- warp instructions per launch (ncu, profiles/) over
+        # the slots the measured duration offers (SMs x 4 schedulers x SM clock)
+        sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        for name, wi in (tdoc.get("_warp_instructions") or {}).items():
+            if name in kernels and wi:
+                kernels[name]["warp_instructions"] = wi
+                kernels[name]["issue_slot_frac"] = wi / (kernels[name]["ms"] * 1e-3 * 148 * 4 * sm_clock)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic,
                 "peak_source": peak_src,
+                "issue_slot_frac": kernels[dom].get("issue_slot_frac"),
                 "note": "algorithmic bytes (SURVEY 8(d) formulas at the measured mean K valid pixels/scan) / "
-                        "CUDA-event duration inside the timed region; see `kernels` for every operator"}
+                        "CUDA-event duration inside the timed region; see `kernels` for every operator. The kernel is "
+                        "instruction-issue bound (exact NN search): `issue_slot_frac` is the fraction of the SMs' "
+                        "issue slots its warp instructions fill"}
 
     # ---------------- CPU baseline: oracle port on a bounded sample --------------------------
     cores = cpu_threads()

@@ -112,6 +112,7 @@ def main():
                 traffic[k] = {
                     "dram_bytes_read": to_bytes(*ms["dram__bytes_read.sum"]),
                     "dram_bytes_write": to_bytes(*ms["dram__bytes_write.sum"]),
+                    "warp_instructions": float(ms["smsp__inst_executed.sum"][0].replace(",", "")),
                 }
                 traffic[k]["dram_bytes"] = traffic[k]["dram_bytes_read"] + traffic[k]["dram_bytes_write"]
             except Exception:
@@ -129,6 +130,9 @@ def main():
             doc["_source"] = (f"{a.out}: dram__bytes_read.sum + dram__bytes_write.sum per launch "
                               "(ncu --set full, one launch per kernel)")
             doc["_per_kernel"] = {k: t["dram_bytes"] for k, t in traffic.items()}
+            # warp instructions per launch of every operator (issue-slot utilisation = this / (time x SMs x 4 x clock))
+            doc["_warp_instructions"] = {op: sum(t["warp_instructions"] for k, t in traffic.items() if k.split("<")[0] in names)
+                                         for op, names in ops.items()}
             with open(a.traffic, "w") as f:
                 json.dump(doc, f, indent=1)
     with open(a.out, "w") as f:
