@@ -127,17 +127,42 @@ __device__ __forceinline__ void accumulate_pair(uint32_t flags, const float4 p, 
     }
 }
 
-// one partial row per warp: shuffle-tree sums, lane k keeps column k (and k+32)
+// Sum of `acc[k]` over the 32 lanes for every k < N, lane k keeping column k (keep0) and column 32 + k (keep1).
+// Columns 0..31 go through a recursive-halving exchange: in the round with offset o the lanes whose bit o is clear
+// keep the lower half of the live columns and receive the partner's contribution to them (31 shuffles for 32
+// columns instead of 32 x 5 for per-column shuffle trees); after the five rounds lane L holds the total of column L.
+// The (few) columns >= 32 use plain shuffle trees.
+template <int N>
+__device__ __forceinline__ void warp_column_sums(const float (&acc)[kIcpAcc], float& keep0, float& keep1) {
+    const int lane = threadIdx.x & 31;
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = (k < N) ? acc[k] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; ++k) {
+            const float send = upper ? v[k] : v[k + o];
+            const float keep = upper ? v[k + o] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    keep0 = v[0];
+    keep1 = 0.0f;
+#pragma unroll
+    for (int k = 32; k < N; ++k) {
+        const float s = warp_sum(acc[k]);
+        if (lane == k - 32) keep1 = s;
+    }
+}
+
+// one partial row per warp, lane k writes column k (and k+32)
 template <int N = kIcpAcc>   // columns >= N are known to be zero (e.g. the po2po block when it is off)
 __device__ __forceinline__ void write_warp_partials(const float (&acc)[kIcpAcc], float* __restrict__ row) {
     const int lane = threadIdx.x & 31;
-    float keep0 = 0.0f, keep1 = 0.0f;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        const float s = warp_sum(acc[k]);
-        if (k < 32) { if (lane == k) keep0 = s; }
-        else        { if (lane == k - 32) keep1 = s; }
-    }
+    float keep0, keep1;
+    warp_column_sums<N>(acc, keep0, keep1);
     row[lane] = keep0;
     if (lane < DELORA_ICP_PARTIAL - 32) row[32 + lane] = keep1;
 }
@@ -146,13 +171,8 @@ __device__ __forceinline__ void write_warp_partials(const float (&acc)[kIcpAcc],
 template <int N = kIcpAcc>
 __device__ __forceinline__ void add_warp_partials(const float (&acc)[kIcpAcc], float* __restrict__ row) {
     const int lane = threadIdx.x & 31;
-    float keep0 = 0.0f, keep1 = 0.0f;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        const float s = warp_sum(acc[k]);
-        if (k < 32) { if (lane == k) keep0 = s; }
-        else        { if (lane == k - 32) keep1 = s; }
-    }
+    float keep0, keep1;
+    warp_column_sums<N>(acc, keep0, keep1);
     row[lane] += keep0;
     if (lane < DELORA_ICP_PARTIAL - 32) row[32 + lane] += keep1;
 }

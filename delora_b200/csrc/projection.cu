@@ -58,6 +58,9 @@ project_scatter_kernel(const float* __restrict__ points, const int32_t* __restri
 }
 
 // One thread resolves 4 consecutive pixels: 2 x 16-byte key loads, float4 stores per channel.
+// CT = compile-time channel count (3: xyz, 4: xyz + reflectance) so that all 4 x CT gathers are issued before
+// the first store (the kernel is latency-bound on them); CT = 0: generic loop.
+template <int CT>
 __global__ void __launch_bounds__(256)
 project_resolve_kernel(const float* __restrict__ points, int C, int n_stride, int HW,
                        unsigned long long* __restrict__ keys, float* __restrict__ image,
@@ -94,15 +97,32 @@ project_resolve_kernel(const float* __restrict__ points, int C, int n_stride, in
         rng[j] = hit ? __uint_as_float((unsigned)(k[j] >> 32)) : 0.0f;
     }
     const bool vec = (p0 + 3 < HW) && ((HW & 3) == 0);
-    for (int c = 0; c < C; ++c) {
-        float val[4];
+    if (CT > 0) {
+        float val[CT > 0 ? CT : 1][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) val[j] = idx[j] >= 0 ? __ldg(pb + (size_t)c * n_stride + idx[j]) : 0.0f;
-        if (vec) {
-            *reinterpret_cast<float4*>(ib + (size_t)c * HW + p0) = make_float4(val[0], val[1], val[2], val[3]);
-        } else {
+        for (int c = 0; c < CT; ++c)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (p0 + j < HW) ib[(size_t)c * HW + p0 + j] = val[j];
+            for (int j = 0; j < 4; ++j) val[c][j] = idx[j] >= 0 ? __ldg(pb + (size_t)c * n_stride + idx[j]) : 0.0f;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            if (vec) {
+                *reinterpret_cast<float4*>(ib + (size_t)c * HW + p0) = make_float4(val[c][0], val[c][1], val[c][2], val[c][3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (p0 + j < HW) ib[(size_t)c * HW + p0 + j] = val[c][j];
+            }
+        }
+    } else {
+        for (int c = 0; c < C; ++c) {
+            float val[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) val[j] = idx[j] >= 0 ? __ldg(pb + (size_t)c * n_stride + idx[j]) : 0.0f;
+            if (vec) {
+                *reinterpret_cast<float4*>(ib + (size_t)c * HW + p0) = make_float4(val[0], val[1], val[2], val[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (p0 + j < HW) ib[(size_t)c * HW + p0 + j] = val[j];
+            }
         }
     }
     if (vec) {
@@ -151,8 +171,12 @@ extern "C" int delora_project_fwd(const float* points, const int32_t* n_points, 
     DELORA_CHECK_LAUNCH("project_scatter_kernel");
     const int HW = H * W;
     dim3 grid2((HW + 1023) / 1024, B);
-    project_resolve_kernel<<<grid2, 256, 0, st>>>(points, C, n_stride, HW, (unsigned long long*)keys, image,
-                                                  index_map);
+    if (C == 3)
+        project_resolve_kernel<3><<<grid2, 256, 0, st>>>(points, C, n_stride, HW, (unsigned long long*)keys, image, index_map);
+    else if (C == 4)
+        project_resolve_kernel<4><<<grid2, 256, 0, st>>>(points, C, n_stride, HW, (unsigned long long*)keys, image, index_map);
+    else
+        project_resolve_kernel<0><<<grid2, 256, 0, st>>>(points, C, n_stride, HW, (unsigned long long*)keys, image, index_map);
     DELORA_CHECK_LAUNCH("project_resolve_kernel");
     return 0;
 }

@@ -117,11 +117,8 @@ def test_sleef_restatement_matches_torch_atan2():
     import ctypes
     import subprocess
     from helpers import ROOT
-    out_dir = os.path.join(ROOT, "oracle", "_ref")
-    os.makedirs(out_dir, exist_ok=True)
-    lib = os.path.join(out_dir, "libsleef_atan2f.so")
-    subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-mfma", "-ffp-contract=off",
-                    os.path.join(ROOT, "oracle", "sleef_atan2f.c"), "-o", lib, "-lm"], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)      # oracle/Makefile -> oracle/_ref/
+    lib = os.path.join(ROOT, "oracle", "_ref", "libsleef_atan2f.so")
     L = ctypes.CDLL(lib)
     L.delora_sleef_atan2f_array.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_long]
 
