@@ -80,16 +80,16 @@ __device__ __forceinline__ void smallest_eigenvector(Sym3 m, float& nx, float& n
 
 // ---------------------------------------------------------------------------------------------
 // Fast path for the reference's 7 x 11 patch (config/config_datasets.yaml:33,60).
-// Tile = 32 columns x 16 rows per CTA of 128 threads; every thread owns FOUR vertically adjacent
-// pixels, so one shared-memory read of a neighbour feeds up to four patches (10 x 11 LDS.128 for
-// 4 x 77 taps: 2.8x less shared-memory traffic than one pixel per thread, which is what bounded
-// the first version: 128 B/clk/SM of LDS.128).  The halo is staged ALREADY CLAMPED (positions
+// Tile = 32 columns x 16 rows per CTA of 256 threads; every thread owns kFastPix = 2 vertically adjacent
+// pixels (one packed fp32x2 pair), so one shared-memory read of a neighbour feeds both patches (8 x 11
+// LDS.128 for 2 x 77 taps).  Four pixels per thread (two pairs, 92 registers, 20 warps/SM) cost the same
+// instructions per pixel and measured 3 % slower than two (62 registers, 32 warps/SM).  The halo is staged ALREADY CLAMPED (positions
 // outside the image replicate the edge pixel, exactly the reference's index clamp,
 // normal_computation.py:104-111), so the tap loops use constant offsets and no index math.
 // tile.w = |p|, or +inf for an all-zero pixel: "neighbour present" (range gate passed and
 // not (0,0,0), linalg.py:34-37) is then the single test !(|q.w - c.w| > eps).
-constexpr int kFastTW = 32, kFastTH = 16, kFastPix = 4, kFastA = 3, kFastB = 5;
-constexpr int kFastThreads = kFastTW * (kFastTH / kFastPix);            // 128
+constexpr int kFastTW = 32, kFastTH = 16, kFastPix = 2, kFastA = 3, kFastB = 5;
+constexpr int kFastThreads = kFastTW * (kFastTH / kFastPix);            // 256
 constexpr int kFastTileW = kFastTW + 2 * kFastB;                        // 42
 constexpr int kFastTileH = kFastTH + 2 * kFastA;                        // 22
 
@@ -126,7 +126,7 @@ normals_7x11_kernel(const float* __restrict__ image, int C_img, int H, int W, fl
         c[k] = base[(k + kFastA) * kFastTileW + kFastB];
         valid[k] = (vb + k < H) && c[k].x != 0.0f && c[k].y != 0.0f && c[k].z != 0.0f;     // :35
     }
-    // The four pixels are processed as two PAIRS in packed fp32x2 arithmetic (Blackwell FFMA2 /
+    // The pixels are processed as PAIRS in packed fp32x2 arithmetic (Blackwell FFMA2 /
     // FADD2 / FMUL2: one instruction per two fp32 lanes, IEEE round-to-nearest per lane, so the
     // numbers are those of the scalar code).  A neighbour outside one pixel's 7 rows gets weight 0.
     constexpr int kPairs = kFastPix / 2;
