@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..data import batching
 from ..data import dataset as dataset_module
 from ..losses import icp_losses
 from ..models import model as model_module
@@ -110,16 +111,40 @@ class Deployer(object):
             f |= ops.LOSS_PL2PL | (ops.NORMAL_LINEAR if self.config["normal_loss"] == "linear" else 0)
         return f
 
+    def _normalize_batch(self, pts, counts_host, b):
+        """`normalize_input` (:222-235) for a padded batch: per sample, the mean of the two scans' mean ranges --
+        each mean reduced over exactly that scan's points, like the reference (the projection downstream is
+        discrete, so the factor must not differ in the last bit)."""
+        means = torch.stack([torch.mean(torch.norm(pts[i:i + 1, :, :n], dim=1), dim=1, keepdim=True)
+                             for i, n in enumerate(counts_host)])                      # [2B,1,1]
+        factor = torch.stack([torch.mean(torch.cat((means[i], means[b + i]), dim=1), dim=1) for i in range(b)]).view(b)
+        pts /= torch.cat((factor, factor)).view(2 * b, 1, 1)
+        return factor
+
     def step(self, preprocessed_dicts, epoch_losses=None, log_images_bool=False):
+        """`preprocessed_dicts`: the reference's list of per-sample dicts, or a `data.batching.PaddedBatch`
+        (already on the device: no per-sample work at all)."""
+        padded = isinstance(preprocessed_dicts, batching.PaddedBatch)
         b = len(preprocessed_dicts)
-        dataset = preprocessed_dicts[0]["dataset"]
+        dataset = preprocessed_dicts.dataset if padded else preprocessed_dicts[0]["dataset"]
         ds = self.config[dataset]
         h, w = ds["vertical_cells"], ds["horizontal_cells"]
         hf, vf = self.config["horizontal_field_of_view"], ds["vertical_field_of_view"]
-        if self.config["normalization_scaling"]:
-            for d in preprocessed_dicts:
-                self.normalize_input(preprocessed_data=d)
-        pts, nrm, cnt = self._stack(preprocessed_dicts)
+        scaling = None
+        if padded:
+            dev = torch.device(self.device)
+            batch = preprocessed_dicts if preprocessed_dicts.flat.device == dev else preprocessed_dicts.to(dev)
+            pts, nrm, cnt = batch.points, batch.normals, batch.counts
+            if self.config["normalization_scaling"]:
+                scaling = self._normalize_batch(pts, batch.counts_host, b)
+            n_last = batch.counts_host[2 * b - 1]
+        else:
+            if self.config["normalization_scaling"]:
+                for d in preprocessed_dicts:
+                    self.normalize_input(preprocessed_data=d)
+                scaling = torch.cat([d["scaling_factor"].reshape(1) for d in preprocessed_dicts]).to(self.device)
+            pts, nrm, cnt = self._stack(preprocessed_dicts)
+            n_last = int(preprocessed_dicts[-1]["scan_2"].shape[2])
         image, index_map = self.img_projection.project_batch(pts, cnt, dataset)    # [2B,4,H,W]
         images_model_1, images_model_2 = image[:b], image[b:]
         self.log_img_1, self.log_img_2 = images_model_1[-1:, :3], images_model_2[-1:, :3]
@@ -129,9 +154,8 @@ class Deployer(object):
             translation=translations, quaternion=rotation_representation, device=self.device)
 
         if self.config["inference_only"]:
-            if self.config["normalization_scaling"]:
-                for i, d in enumerate(preprocessed_dicts):
-                    computed_transformations[i, :3, 3] *= d["scaling_factor"]
+            if scaling is not None:
+                computed_transformations[:, :3, 3] *= scaling.view(b, 1)
             return computed_transformations
 
         pts_grid, nrm_grid = ops.grids_from_projection(pts, nrm, index_map)
@@ -157,13 +181,11 @@ class Deployer(object):
         if self.training_bool:
             loss.sum().backward()
             self.optimizer.step()
-        if self.config["normalization_scaling"]:
-            for i, d in enumerate(preprocessed_dicts):
-                computed_transformations[i, :3, 3] *= d["scaling_factor"]
+        if scaling is not None:
+            computed_transformations[:, :3, 3] *= scaling.view(b, 1)
         if epoch_losses is not None:
             # `visible_pixels` (:365-367): points of the last transformed source scan with 0 < v < H
             with torch.no_grad():
-                n_last = int(preprocessed_dicts[-1]["scan_2"].shape[2])
                 src = pts[2 * b - 1:2 * b, :, :n_last]
                 moved = self.transform_point_cloud_transformation_matrix(computed_transformations[-1:].detach(), src)
                 _, v_pix, _ = ops.project_uv(moved.contiguous(), cnt[2 * b - 1:2 * b].contiguous(), h, w, hf, vf)

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import deployer
+from ..data import batching
 from ..parallel_grad import FlatGradAllReduce
 
 try:
@@ -52,10 +53,11 @@ class Trainer(deployer.Deployer):
     def train_epoch(self, epoch, dataloader):
         epoch_losses = self.new_epoch_losses()
         for counter, preprocessed_dicts in enumerate(dataloader):
-            for d in preprocessed_dicts:
-                for key in d:
-                    if hasattr(d[key], "to"):
-                        d[key] = d[key].to(self.device)
+            if not isinstance(preprocessed_dicts, batching.PaddedBatch):          # reference collate: list of dicts
+                for d in preprocessed_dicts:
+                    for key in d:
+                        if hasattr(d[key], "to"):
+                            d[key] = d[key].to(self.device)
             self.optimizer.zero_grad()
             epoch_losses, _ = self.step(preprocessed_dicts=preprocessed_dicts, epoch_losses=epoch_losses,
                                         log_images_bool=False)
@@ -69,11 +71,17 @@ class Trainer(deployer.Deployer):
 
     def train(self, max_epochs=10000):
         sampler = self._sampler()
+        on_gpu = str(self.config["device"]).startswith("cuda")
+        # config["device_batching"] (default on): workers pack each batch into one pinned staging buffer and the
+        # copy of batch i+1 overlaps step i (data/batching.py); off = the reference's list-of-dicts collate
+        device_batching = bool(self.config.get("device_batching", True))
         dataloader = torch.utils.data.DataLoader(dataset=self.dataset, batch_size=self.batch_size,
                                                  shuffle=sampler is None, sampler=sampler,
-                                                 collate_fn=Trainer.list_collate,
+                                                 collate_fn=batching.padded_collate if device_batching else Trainer.list_collate,
                                                  num_workers=self.config["num_dataloader_workers"],
-                                                 pin_memory=str(self.config["device"]).startswith("cuda"))
+                                                 pin_memory=on_gpu)
+        if device_batching:
+            dataloader = batching.PrefetchLoader(dataloader, self.config["device"])
         run = None
         if mlflow is not None and self.grad_sync.rank == 0:
             mlflow.set_experiment(self.config["experiment"])

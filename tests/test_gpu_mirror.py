@@ -296,3 +296,33 @@ def test_tester_inference_collects_transforms(tmp_path, cuda_lib):
     cfg["checkpoint"] = None
     with pytest.raises(Exception, match="No checkpoint"):
         Tester(config=cfg)
+
+
+@pytest.mark.parametrize("scaling", [False, True])
+def test_step_with_padded_batch_equals_list_of_dicts(scaling, tmp_path, cuda_lib):
+    """Device-side batching (data/batching.py): `Deployer.step(PaddedBatch)` must give exactly what the reference-shaped
+    list-of-dicts path gives (same kernels, same inputs), with and without `normalization_scaling`."""
+    from delora_b200.data import batching
+    from delora_b200.deploy.trainer import Trainer
+    write_preprocessed(tmp_path, n_scans=4)
+    cfg = tiny_training_config(tmp_path, batch_size=3)
+    cfg["normalization_scaling"] = scaling
+    torch.manual_seed(0)
+    trainer = Trainer(config=cfg)
+    trainer.training_bool = False
+    items = [trainer.dataset[i] for i in range(3)]
+    padded = batching.padded_collate([trainer.dataset[i] for i in range(3)]).to(DEV)
+    for d in items:
+        for k in d:
+            if hasattr(d[k], "to"):
+                d[k] = d[k].to(DEV)
+    el_a, t_a = trainer.step(preprocessed_dicts=items, epoch_losses=Trainer.new_epoch_losses())
+    el_b, t_b = trainer.step(preprocessed_dicts=padded, epoch_losses=Trainer.new_epoch_losses())
+    assert torch.equal(t_a, t_b)
+    for k in ("loss_epoch", "loss_point_cloud_epoch", "loss_po2pl_epoch", "loss_pl2pl_epoch", "visible_pixels_epoch"):
+        assert np.array_equal(np.asarray(el_a[k]), np.asarray(el_b[k])), k
+    # the prefetching loader feeds the trainer end to end
+    cfg2 = tiny_training_config(tmp_path, batch_size=2)
+    trainer2 = Trainer(config=cfg2)
+    hist = trainer2.train(max_epochs=1)
+    assert len(hist) == 1 and np.isfinite(hist[0])

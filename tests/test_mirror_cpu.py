@@ -162,3 +162,29 @@ def test_compute_poses_golden(tmp_path):
     poses.write_poses_to_text_file(str(tmp_path / "poses.txt"), out)
     rows = np.loadtxt(tmp_path / "poses.txt")
     assert rows.shape == (41, 12) and np.allclose(rows, out.reshape(41, 16)[:, :12])
+
+
+def test_padded_collate_and_prefetch_host_logic():
+    """data.batching: list of dataset items -> one staging buffer with [2B,3,Nmax] points / normals + counts
+    (scan_1 of every sample first, then scan_2), zero padding, metadata kept; PrefetchLoader on CPU is a pass-through."""
+    from delora_b200.data import batching
+    g = torch.Generator().manual_seed(5)
+    items = []
+    for i, (n1, n2) in enumerate(((7, 5), (3, 9), (6, 6))):
+        items.append({"index": i, "index_dataset": 0, "index_sequence": 1, "index_scan": i, "dataset": "kitti",
+                      "scan_1": torch.randn(1, 3, n1, generator=g), "scan_2": torch.randn(1, 3, n2, generator=g),
+                      "normal_list_1": torch.randn(1, 3, n1, generator=g), "normal_list_2": torch.randn(1, 3, n2, generator=g)})
+    batch = batching.padded_collate(items)
+    assert len(batch) == 3 and batch.n_max == 9 and batch.dataset == "kitti"
+    assert batch.points.shape == (6, 3, 9) and batch.counts.tolist() == [7, 3, 6, 5, 9, 6]
+    for i, d in enumerate(items):
+        assert torch.equal(batch.points[i, :, :d["scan_1"].shape[2]], d["scan_1"][0])
+        assert torch.equal(batch.points[3 + i, :, :d["scan_2"].shape[2]], d["scan_2"][0])
+        assert torch.equal(batch.normals[3 + i, :, :d["scan_2"].shape[2]], d["normal_list_2"][0])
+        assert float(batch.points[i, :, d["scan_1"].shape[2]:].abs().sum()) == 0.0
+        assert batch.meta[i]["index_scan"] == i and "scan_1" not in batch.meta[i]
+    # views alias one flat buffer (a single copy ships everything)
+    assert batch.points.data_ptr() == batch.flat.data_ptr()
+    loader = torch.utils.data.DataLoader(items, batch_size=2, collate_fn=batching.padded_collate)
+    out = list(batching.PrefetchLoader(loader, "cpu"))
+    assert [len(b) for b in out] == [2, 1] and out[1].counts.tolist() == [6, 6]
