@@ -706,6 +706,25 @@ nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, in
     y[i] = __bfloat162float(x[(((size_t)b * (H + 2) + h + 1) * (W + 2) + w + 1) * C + c]);
 }
 
+// fp32 torch filter [Cout, Cin, k, k] -> the two bf16 layouts the convolution kernels read, in one launch:
+//   w_fwd [Cout, k*k, Cin_pad]  (tap-major K of fprop; channels >= Cin zero)
+//   w_flip[Cin,  k*k, Cout]     (filter of the data-gradient convolution: spatially flipped, in/out swapped)
+__global__ void __launch_bounds__(256)
+weight_prep_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Cin_pad, __nv_bfloat16* __restrict__ w_fwd,
+                   __nv_bfloat16* __restrict__ w_flip) {
+    const int taps = k * k;
+    const size_t n_fwd = (size_t)Cout * taps * Cin_pad, n_flip = w_flip ? (size_t)Cin * taps * Cout : 0;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n_fwd) {
+        const int ci = (int)(i % Cin_pad), tap = (int)((i / Cin_pad) % taps), co = (int)(i / ((size_t)Cin_pad * taps));
+        w_fwd[i] = __float2bfloat16_rn(ci < Cin ? __ldg(w + ((size_t)co * Cin + ci) * taps + tap) : 0.0f);
+    } else if (i < n_fwd + n_flip) {
+        const size_t j = i - n_fwd;
+        const int co = (int)(j % Cout), tap = (int)((j / Cout) % taps), ci = (int)(j / ((size_t)Cout * taps));
+        w_flip[j] = __float2bfloat16_rn(__ldg(w + ((size_t)co * Cin + ci) * taps + (taps - 1 - tap)));
+    }
+}
+
 // ---------------------------------------------------------------- host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -823,6 +842,17 @@ extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void
     conv_fprop_tc_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(
         maps->x, maps->w, (const __nv_bfloat16*)residual, (const __nv_bfloat16*)saved, (__nv_bfloat16*)y, p);
     DELORA_CHECK_LAUNCH("conv_fprop_tc_kernel");
+    return 0;
+}
+
+extern "C" int delora_conv_weight_prep_bf16(const float* w, int Cout, int Cin, int ksize, int Cin_pad, void* w_fwd,
+                                            void* w_flip, void* stream) {
+    DELORA_CHECK_ARG(w && w_fwd && Cout > 0 && Cin > 0 && Cin_pad >= Cin && (ksize == 1 || ksize == 3),
+                     "delora_conv_weight_prep_bf16: bad argument");
+    const size_t total = (size_t)Cout * ksize * ksize * Cin_pad + (w_flip ? (size_t)Cin * ksize * ksize * Cout : 0);
+    weight_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        w, Cout, Cin, ksize, Cin_pad, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_flip);
+    DELORA_CHECK_LAUNCH("weight_prep_kernel");
     return 0;
 }
 

@@ -84,6 +84,9 @@ class OdometryStream:
             torch.cuda.current_stream().synchronize()
             self.frames += 1
             return None
+        tc = self.model._tensor_core_path()
+        if tc is not None:
+            tc._refresh_weights()                # bf16 filter copies follow the fp32 parameters (no-op when unchanged)
         if self.use_cuda_graph:
             if self.graph is None:
                 self._capture()

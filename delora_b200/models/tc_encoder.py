@@ -17,21 +17,6 @@ import torch
 from .. import ops
 
 
-def _prep(weight, cin_pad=None):
-    """[Cout,Cin,k,k] fp32 -> [Cout, k*k, Cin_pad] bf16 (tap-major K)."""
-    cout, cin, k, _ = weight.shape
-    w = weight.detach().permute(0, 2, 3, 1).reshape(cout, k * k, cin)
-    if cin_pad is not None and cin_pad > cin:
-        w = torch.nn.functional.pad(w, (0, cin_pad - cin))
-    return w.contiguous().to(torch.bfloat16)
-
-
-def _prep_flip(weight):
-    """Filter of the data-gradient convolution: [Cout,Cin,k,k] -> [Cin, k*k (flipped), Cout] bf16."""
-    cout, cin, k, _ = weight.shape
-    return weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k, cout).contiguous().to(torch.bfloat16)
-
-
 class _EncoderTrainFn(torch.autograd.Function):
     """Differentiable encoder trunk on the tcgen05 kernels: images -> pooled [B, C4] features.
     forward = TensorCoreEncoder chain with the activations kept; backward = per BasicBlock (reverse order)
@@ -60,16 +45,51 @@ class TensorCoreEncoder:
         if r.conv1.weight.shape[0] % 64 != 0:
             raise Exception("tensor-core encoder needs channel counts that are multiples of 64 "
                             "(factor_fewer_resnet_channels = 1)")
-        self.w_stem = _prep(r.conv1.weight, 64)
         self.blocks = []
         for li in range(1, 5):
             for blk in getattr(r, f"layer{li}"):
                 stride = blk.stride if isinstance(blk.stride, tuple) else (blk.stride, blk.stride)
-                self.blocks.append({
-                    "w1": _prep(blk.conv1.weight), "w2": _prep(blk.conv2.weight),
-                    "wd": _prep(blk.downsample[0].weight) if blk.downsample is not None else None,
-                    "stride": stride, "cout": blk.conv1.weight.shape[0]})
+                self.blocks.append({"has_wd": blk.downsample is not None, "stride": stride,
+                                    "cout": blk.conv1.weight.shape[0]})
+        # persistent bf16 copies of the filters in the two layouts the kernels read (fprop / dgrad); rewritten by one
+        # small kernel per layer whenever the fp32 parameters change (every training step; after load_state_dict)
+        self._wbufs = None
+        self._wversion = None
         self._buf = {}
+
+    def _weight_buffers(self):
+        params = self.trunk_parameters()
+        if self._wbufs is None or self._wbufs[0][0].device != params[0].device:
+            bufs = []
+            for i, p_ in enumerate(params):
+                cout, cin, k, _ = p_.shape
+                cin_pad = 64 if i == 0 else cin
+                fwd = torch.empty((cout, k * k, cin_pad), dtype=torch.bfloat16, device=p_.device)
+                flip = None if i == 0 else torch.empty((cin, k * k, cout), dtype=torch.bfloat16, device=p_.device)
+                bufs.append((fwd, flip, cin_pad))
+            self._wbufs, self._wversion = bufs, None
+        return params, self._wbufs
+
+    def _refresh_weights(self, force=False):
+        """-> list of (w_fwd, w_flip) per trunk parameter, up to date with the fp32 parameters."""
+        params, bufs = self._weight_buffers()
+        version = tuple(p_._version for p_ in params) + tuple(p_.data_ptr() for p_ in params)
+        if force or version != self._wversion:
+            for p_, (fwd, flip, cin_pad) in zip(params, bufs):
+                ops.conv_weight_prep(p_, fwd, flip, cin_pad)
+            self._wversion = version
+        return bufs
+
+    def _block_weights(self, bufs):
+        """Regroup the flat per-parameter list into (stem, [per block dict])."""
+        it = iter(bufs)
+        stem = next(it)
+        out = []
+        for blk in self.blocks:
+            w1, w2 = next(it), next(it)
+            wd = next(it) if blk["has_wd"] else None
+            out.append({"w1": w1, "w2": w2, "wd": wd})
+        return stem, out
 
     def _buffer(self, tag, b, h, w, c, device):
         key = (tag, b, h, w, c)
@@ -84,9 +104,10 @@ class TensorCoreEncoder:
         """-> [x1, x2, x3, x4] as padded NHWC bf16 + their (H, W)."""
         b, _, h, w = image_1.shape
         dev = image_1.device
+        stem_w, blk_w = self._block_weights(self._refresh_weights())
         x = ops.images_to_nhwc(image_1.float().contiguous(), image_2.float().contiguous(), 64)
         w2 = ops.conv_out_size(w, 2)
-        y = ops.conv2d_fprop(x, self.w_stem, h, w, 3, (1, 2), self.act, None, self._buffer("stem", b, h, w2, 64, dev))
+        y = ops.conv2d_fprop(x, stem_w[0], h, w, 3, (1, 2), self.act, None, self._buffer("stem", b, h, w2, 64, dev))
         w4 = w2 // 2
         cur = self._buffer("pool", b, h, w4, 64, dev)
         L = ops._lib.lib()
@@ -97,14 +118,15 @@ class TensorCoreEncoder:
         for i, blk in enumerate(self.blocks):
             sh, sw = blk["stride"]
             oh, ow, co = ops.conv_out_size(ch, sh), ops.conv_out_size(cw, sw), blk["cout"]
-            t1 = ops.conv2d_fprop(cur, blk["w1"], ch, cw, 3, (sh, sw), self.act, None,
+            bw = blk_w[i]
+            t1 = ops.conv2d_fprop(cur, bw["w1"][0], ch, cw, 3, (sh, sw), self.act, None,
                                   self._buffer(f"b{i}a", b, oh, ow, co, dev))
-            if blk["wd"] is not None:
-                ident = ops.conv2d_fprop(cur, blk["wd"], ch, cw, 1, (sh, sw), ops.ACT_NONE, None,
+            if bw["wd"] is not None:
+                ident = ops.conv2d_fprop(cur, bw["wd"][0], ch, cw, 1, (sh, sw), ops.ACT_NONE, None,
                                          self._buffer(f"b{i}d", b, oh, ow, co, dev))
             else:
                 ident = cur
-            cur = ops.conv2d_fprop(t1, blk["w2"], oh, ow, 3, (1, 1), self.act, ident,
+            cur = ops.conv2d_fprop(t1, bw["w2"][0], oh, ow, 3, (1, 1), self.act, ident,
                                    self._buffer(f"b{i}o", b, oh, ow, co, dev))
             ch, cw = oh, ow
             if i % 2 == 1:
@@ -151,9 +173,10 @@ class TensorCoreEncoder:
         it = iter(weights)
         st = {"B": b, "H": h, "W": w, "blocks": []}
         w_stem = next(it)
+        stem_w, blk_w = self._block_weights(self._refresh_weights(force=True))    # bf16 filters of THIS step's weights
         st["x_in"] = ops.images_to_nhwc(image_1, image_2, 64)
         w2 = ops.conv_out_size(w, 2)
-        st["y0"] = ops.conv2d_fprop(st["x_in"], _prep(w_stem, 64), h, w, 3, (1, 2), self.act, None,
+        st["y0"] = ops.conv2d_fprop(st["x_in"], stem_w[0], h, w, 3, (1, 2), self.act, None,
                                     self._buffer("t_stem", b, h, w2, 64, dev))
         w4 = w2 // 2
         st["p0"] = self._buffer("t_pool", b, h, w4, 64, dev)
@@ -164,19 +187,21 @@ class TensorCoreEncoder:
         cur, ch, cw = st["p0"], h, w4
         for i, blk in enumerate(self.blocks):
             w1, wc2 = next(it), next(it)
-            wd = next(it) if blk["wd"] is not None else None
+            wd = next(it) if blk["has_wd"] else None
+            bw = blk_w[i]
             sh, sw = blk["stride"]
             oh, ow, co = ops.conv_out_size(ch, sh), ops.conv_out_size(cw, sw), blk["cout"]
-            t1 = ops.conv2d_fprop(cur, _prep(w1), ch, cw, 3, (sh, sw), self.act, None,
+            t1 = ops.conv2d_fprop(cur, bw["w1"][0], ch, cw, 3, (sh, sw), self.act, None,
                                   self._buffer(f"t{i}a", b, oh, ow, co, dev))
             if wd is not None:
-                ident = ops.conv2d_fprop(cur, _prep(wd), ch, cw, 1, (sh, sw), ops.ACT_NONE, None,
+                ident = ops.conv2d_fprop(cur, bw["wd"][0], ch, cw, 1, (sh, sw), ops.ACT_NONE, None,
                                          self._buffer(f"t{i}d", b, oh, ow, co, dev))
             else:
                 ident = cur
-            out = ops.conv2d_fprop(t1, _prep(wc2), oh, ow, 3, (1, 1), self.act, ident,
+            out = ops.conv2d_fprop(t1, bw["w2"][0], oh, ow, 3, (1, 1), self.act, ident,
                                    self._buffer(f"t{i}o", b, oh, ow, co, dev))
             st["blocks"].append({"x": cur, "t1": t1, "out": out, "w1": w1, "w2": wc2, "wd": wd, "stride": (sh, sw),
+                                 "f1": bw["w1"][1], "f2": bw["w2"][1], "fd": bw["wd"][1] if bw["wd"] is not None else None,
                                  "in_hw": (ch, cw), "out_hw": (oh, ow)})
             cur, ch, cw = out, oh, ow
         st["w_stem"] = w_stem
@@ -204,23 +229,23 @@ class TensorCoreEncoder:
             (ch, cw), (oh, ow), (sh, sw) = blk["in_hw"], blk["out_hw"], blk["stride"]
             cin, cout = blk["x"].shape[3], blk["out"].shape[3]
             g_w2 = ops.conv2d_wgrad(blk["t1"], dz2, oh, ow, 3, (1, 1))
-            dz1 = ops.conv2d_fprop(dz2, _prep_flip(blk["w2"]), oh, ow, 3, (1, 1), act_bwd, None,
+            dz1 = ops.conv2d_fprop(dz2, blk["f2"], oh, ow, 3, (1, 1), act_bwd, None,
                                    self._buffer(f"g{i}a", b, oh, ow, cout, dev), saved=blk["t1"])
             g_w1 = ops.conv2d_wgrad(blk["x"], dz1, ch, cw, 3, (sh, sw))
             g_wd = None
             if blk["wd"] is not None:
                 g_wd = ops.conv2d_wgrad(blk["x"], dz2, ch, cw, 1, (sh, sw))
                 up2 = ops.zero_upsample(dz2, oh, ow, (sh, sw), self._buffer(f"g{i}u2", b, ch, cw, cout, dev), (ch, cw))
-                resid = ops.conv2d_fprop(up2, _prep_flip(blk["wd"]), ch, cw, 1, (1, 1), ops.ACT_NONE, None,
+                resid = ops.conv2d_fprop(up2, blk["fd"], ch, cw, 1, (1, 1), ops.ACT_NONE, None,
                                          self._buffer(f"g{i}d", b, ch, cw, cin, dev))
                 src = ops.zero_upsample(dz1, oh, ow, (sh, sw), self._buffer(f"g{i}u1", b, ch, cw, cout, dev), (ch, cw))
             else:
                 resid, src = dz2, dz1
             if i > 0:     # the block input is the previous block's activation output: fold act' into the epilogue
-                dz2 = ops.conv2d_fprop(src, _prep_flip(blk["w1"]), ch, cw, 3, (1, 1), act_bwd, resid,
+                dz2 = ops.conv2d_fprop(src, blk["f1"], ch, cw, 3, (1, 1), act_bwd, resid,
                                        self._buffer(f"g{i}x", b, ch, cw, cin, dev), saved=blk["x"])
             else:         # the first block reads the max-pool output
-                d_pool = ops.conv2d_fprop(src, _prep_flip(blk["w1"]), ch, cw, 3, (1, 1), ops.ACT_NONE, resid,
+                d_pool = ops.conv2d_fprop(src, blk["f1"], ch, cw, 3, (1, 1), ops.ACT_NONE, resid,
                                           self._buffer("g_pool", b, ch, cw, cin, dev))
             grads_rev.append((g_w1, g_w2, g_wd))
         h, w = st["H"], st["W"]

@@ -332,6 +332,17 @@ def zero_upsample(x, h, w, stride, out=None, out_hw=None):
     return out
 
 
+def conv_weight_prep(weight, w_fwd, w_flip=None, cin_pad=None):
+    """weight [Cout,Cin,k,k] fp32 -> w_fwd [Cout,k*k,Cin_pad] bf16 and (optional) w_flip [Cin,k*k,Cout] bf16, in place."""
+    cout, cin, k, _ = weight.shape
+    cin_pad = cin if cin_pad is None else int(cin_pad)
+    L = _lib.lib()
+    _lib.check(L.delora_conv_weight_prep_bf16(_req(weight.detach(), torch.float32, "weight"), cout, cin, k, cin_pad,
+                                              w_fwd.data_ptr(), w_flip.data_ptr() if w_flip is not None else None,
+                                              _stream()), "delora_conv_weight_prep_bf16")
+    return w_fwd, w_flip
+
+
 def images_to_nhwc(image_1, image_2, cpad=64):
     b, _, h, w = image_1.shape
     x = torch.empty((b, h + 2, w + 2, cpad), dtype=torch.bfloat16, device=image_1.device)

@@ -99,6 +99,15 @@ def test_tensor_core_encoder_matches_torch_model(h, w, cuda_lib):
     with torch.no_grad():
         t2, q2 = model(image_1=img1, image_2=img2)
     assert torch.equal(t2, t) and torch.equal(q2, q)
+    # the bf16 filter copies follow the fp32 parameters (optimizer steps, load_state_dict): no stale weights
+    with torch.no_grad():
+        model.resnet.layer3[0].conv1.weight.mul_(0.5)
+        model.resnet.conv1.weight.add_(0.01)
+        t3, q3 = model(image_1=img1, image_2=img2)
+        model.config["use_tensor_core_encoder"] = False
+        t3_ref, q3_ref = model(image_1=img1, image_2=img2)
+    assert not torch.equal(t3, t2)
+    assert (t3 - t3_ref).abs().max().item() < 2e-2 and (q3 - q3_ref).abs().max().item() < 2e-2
 
 
 @pytest.mark.parametrize("b,cin,cout,h,w,k,stride", [
