@@ -276,8 +276,27 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
                 const int n = e_lf + e_rt + 1;
                 if (STATS) n_cells += n;
                 int col = wrap_col(cc - e_lf, W);
-#pragma unroll 4
-                for (int k = 0; k < n; ++k) {
+                // n is odd and >= 5 on grids at least 5 wide (the window starts 5 wide and grows by 2): a first batch
+                // of 5 independent loads, then batches of 4 and at most one of 2 -- no generic remainder loop
+                int k = 0;
+                if (n >= 5) {
+                    int cols[5];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) { cols[j] = col; ++col; col = (col == W) ? 0 : col; }
+#pragma unroll
+                    for (int j = 0; j < 5; ++j)
+                        nn2_eval(__ldg(tg + (unsigned)(rbase + cols[j])), rbase + cols[j], sx, sy, sz, nn, rok);
+                    k = 5;
+                }
+                for (; k + 4 <= n; k += 4) {
+                    int cols[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { cols[j] = col; ++col; col = (col == W) ? 0 : col; }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        nn2_eval(__ldg(tg + (unsigned)(rbase + cols[j])), rbase + cols[j], sx, sy, sz, nn, rok);
+                }
+                for (; k < n; ++k) {
                     nn2_eval(__ldg(tg + (unsigned)(rbase + col)), rbase + col, sx, sy, sz, nn, rok);
                     ++col;
                     col = (col == W) ? 0 : col;

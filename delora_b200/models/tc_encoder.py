@@ -235,9 +235,11 @@ class TensorCoreEncoder:
             g_wd = None
             if blk["wd"] is not None:
                 g_wd = ops.conv2d_wgrad(blk["x"], dz2, ch, cw, 1, (sh, sw))
-                up2 = ops.zero_upsample(dz2, oh, ow, (sh, sw), self._buffer(f"g{i}u2", b, ch, cw, cout, dev), (ch, cw))
-                resid = ops.conv2d_fprop(up2, blk["fd"], ch, cw, 1, (1, 1), ops.ACT_NONE, None,
-                                         self._buffer(f"g{i}d", b, ch, cw, cin, dev))
+                # 1x1 strided downsample: its data gradient is the 1x1 convolution of the SMALL dz, scattered to the
+                # strided positions afterwards (2-4x fewer MMAs than convolving the zero-upsampled gradient)
+                small = ops.conv2d_fprop(dz2, blk["fd"], oh, ow, 1, (1, 1), ops.ACT_NONE, None,
+                                         self._buffer(f"g{i}ds", b, oh, ow, cin, dev))
+                resid = ops.zero_upsample(small, oh, ow, (sh, sw), self._buffer(f"g{i}d", b, ch, cw, cin, dev), (ch, cw))
                 src = ops.zero_upsample(dz1, oh, ow, (sh, sw), self._buffer(f"g{i}u1", b, ch, cw, cout, dev), (ch, cw))
             else:
                 resid, src = dz2, dz1
