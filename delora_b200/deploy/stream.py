@@ -31,6 +31,7 @@ class OdometryStream:
         self.host_scan = torch.zeros((1, 3, self.n_max), dtype=torch.float32).pin_memory()
         self.host_count = torch.zeros((1,), dtype=torch.int32).pin_memory()
         self.host_T = torch.zeros((1, 4, 4), dtype=torch.float32).pin_memory()
+        self._host_scan_np, self._host_count_np = self.host_scan.numpy(), self.host_count.numpy()
         self.points = torch.zeros((1, 3, self.n_max), dtype=torch.float32, device=self.device)
         self.count = torch.zeros((1,), dtype=torch.int32, device=self.device)
         self.prev_image = torch.zeros((1, 4, self.h, self.w), dtype=torch.float32, device=self.device)
@@ -72,8 +73,10 @@ class OdometryStream:
         n = int(scan.shape[1])
         if n > self.n_max:
             raise Exception("scan has more points than the stream was sized for")
-        self.host_scan[0, :, :n] = scan[:3]
-        self.host_count[0] = n
+        # plain memcpy into the pinned staging buffer: a torch copy of this size wakes the intra-op thread pool, whose
+        # spinning workers can exhaust a container's CPU quota and stall the stream for tens of ms every 100 ms
+        np.copyto(self._host_scan_np[0, :, :n], scan[:3].numpy())
+        self._host_count_np[0] = n
         self.points.copy_(self.host_scan, non_blocking=True)
         self.count.copy_(self.host_count, non_blocking=True)
         first = self.frames == 0
