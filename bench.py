@@ -382,9 +382,9 @@ def run_ours(args):
                 "peak_source": peak_src,
                 "issue_slot_frac": kernels[dom].get("issue_slot_frac"),
                 "note": "algorithmic bytes (SURVEY 8(d) formulas at the measured mean K valid pixels/scan) / "
-                        "CUDA-event duration inside the timed region; see `kernels` for every operator. The kernel is "
-                        "instruction-issue bound (exact NN search): `issue_slot_frac` is the fraction of the SMs' "
-                        "issue slots its warp instructions fill"}
+                        "CUDA-event duration inside the timed region; see `kernels` for every operator. All three "
+                        "operators are bound by instruction issue / the FP32 pipe, not by HBM (DESIGN.md 4.1-4.3): "
+                        "`issue_slot_frac` is the fraction of the SMs' issue slots the operator's warp instructions fill"}
 
     # ---------------- CPU baseline: oracle port on a bounded sample --------------------------
     cores = cpu_threads()
