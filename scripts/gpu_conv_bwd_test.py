@@ -35,7 +35,7 @@ def run(b, cin, cout, h, w, k, stride):
     wf = wt.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k, cout).contiguous().to(torch.bfloat16)
     dzn = to_padded_nhwc(dz)
     if stride != (1, 1):
-        dzn = ops.zero_upsample(dzn, ho, wo, stride)
+        dzn = ops.zero_upsample(dzn, ho, wo, stride, out_hw=(h, w))
     dx = ops.conv2d_fprop(dzn, wf, h, w, k, (1, 1), ops.ACT_NONE)
     torch.cuda.synchronize()
     got = ops.nhwc_to_nchw(dx, h, w)
