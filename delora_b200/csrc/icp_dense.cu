@@ -649,11 +649,7 @@ extern "C" int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_
         DELORA_CHECK_LAUNCH("block_range_kernel");
     }
     // persistent second kernel: enough CTAs for one wave, never more than there can be items
-    int pend_threads = kPendThreads, pend_mult = 4;
-    if (const char* e = getenv("DELORA_ICP_PEND_THREADS")) pend_threads = atoi(e);   // tuning knobs (profiling only)
-    if (const char* e = getenv("DELORA_ICP_PEND_MULT")) pend_mult = atoi(e);
-    DELORA_CHECK_ARG(pend_threads >= 32 && pend_threads <= 256 && pend_threads % 32 == 0 && pend_mult >= 1,
-                     "DELORA_ICP_PEND_THREADS / DELORA_ICP_PEND_MULT out of range");
+    const int pend_threads = kPendThreads, pend_mult = 4;     // measured flat over 128-256 threads x 4-16 CTAs per SM
     const int pend_grid = (int)std::min<long long>(((long long)B * rows * 32 + 7) / 8, (long long)pend_mult * kNumSMs);
 #define DELORA_LAUNCH_DENSE(PO2PO, STATS)                                                                           \
     do {                                                                                                            \
