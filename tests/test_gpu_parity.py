@@ -370,6 +370,38 @@ def test_dense_icp_arbitrary_transforms_vs_kdtree(name, n_transforms, golden, cu
         assert float(losses[0, 2]) == pytest.approx(float(lo["loss_pl2pl"]), rel=2e-5), (k, ang, tm[:3, 3])
 
 
+def test_dense_icp_handover_limit_and_determinism(golden, cuda_lib, monkeypatch):
+    """The two-kernel split is an implementation detail: any hand-over limit (DELORA_ICP_MAX_STRIPS) must give the
+    same pairs and, up to fp32 summation order, the same losses / gradient; and for a fixed limit repeated calls are
+    BIT-identical although the work list of the second kernel is appended by atomics in arbitrary order."""
+    from delora_b200 import ops, synthetic
+    meta, cfg, _, _, _, out = oracle_case("kitti_64x720", golden)
+    h, w = meta["H"], meta["W"]
+    hf, vf = fov(cfg)
+    images = torch.cat((out["image_1"], out["image_2"])).to(DEV)
+    _, pg, ng = ops.normals(images, grids=True)
+    t = torch.from_numpy(synthetic.transform_matrix(0.6, -0.2, 0.05, math.radians(2.0), 0.0, 0.0)).float()
+    T = t[:3, :].reshape(1, 12).contiguous().to(DEV)
+    scratch = ops.icp_scratch(1, h * w, DEV)
+
+    def run():
+        losses, grad = ops.icp_dense_fwd_bwd(pg[1:2].contiguous(), ng[1:2].contiguous(), T, pg[0:1].contiguous(),
+                                             ng[0:1].contiguous(), h, w, hf, vf, scratch=scratch)
+        return losses.cpu().clone(), grad.cpu().clone()
+
+    base = run()
+    for _ in range(3):
+        again = run()
+        assert torch.equal(again[0], base[0]) and torch.equal(again[1], base[1])
+    for limit in ("0", "3", "100000"):
+        monkeypatch.setenv("DELORA_ICP_MAX_STRIPS", limit)
+        losses, grad = run()
+        assert float(losses[0, 3]) == float(base[0][0, 3]), limit
+        assert torch.allclose(losses[0, :3], base[0][0, :3], rtol=2e-6, atol=0), limit
+        assert torch.allclose(grad, base[1], rtol=1e-4, atol=1e-8), limit
+    monkeypatch.delenv("DELORA_ICP_MAX_STRIPS")
+
+
 def test_generic_lists_shuffled_and_po2po(golden, cuda_lib):
     """Arbitrary (shuffled, with out-of-FOV points) lists through delora_grid_build; po2po on."""
     from delora_b200 import ops
