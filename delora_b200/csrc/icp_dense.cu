@@ -207,6 +207,10 @@ icp_dense_kernel(const float4* __restrict__ src_grid, const float4* __restrict__
                  const float* __restrict__ T, const float4* __restrict__ tgt_grid,
                  const float4* __restrict__ tgt_ngrid, int max_strips, GridParams g, uint32_t flags,
                  float* __restrict__ partial_rows, int rows_per_pair, PendingList pend) {
+    // Programmatic dependent launch: the range-pyramid kernel that follows in the stream reads nothing this kernel
+    // writes, so it may start as soon as every CTA of this grid has been scheduled (it then fills the SMs that the
+    // last, partially filled wave leaves idle).  A no-op unless the next launch opts in.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int b = blockIdx.y;
     const int H = g.H, W = g.W, HW = H * W;
     const float4* __restrict__ tg = tgt_grid + (size_t)b * HW;
@@ -615,6 +619,24 @@ extern "C" int delora_icp_stats(uint32_t* out32, int reset) {
     return 0;
 }
 
+// The range pyramid of the target grids is independent of the window-search kernel launched just before it:
+// programmatic stream serialization lets it overlap that kernel's tail (icp_dense_kernel issues
+// griddepcontrol.launch_dependents); the block-search kernel after it is a normal launch and waits for both.
+static cudaError_t launch_block_range(cudaStream_t st, const float4* tgt_grid, int B, int H, int W, int nbh, int nbw,
+                                      float2* blk) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((nbh * nbw * 32 + 255) / 256, B);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, block_range_kernel, tgt_grid, H, W, nbh, nbw, blk);
+}
+
 extern "C" int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_f4* src_ngrid, const float* T,
                                         const delora_f4* tgt_grid, const delora_f4* tgt_ngrid, int B, int H, int W,
                                         double hfov0, double hfov1, double vfov0, double vfov1, float lambda_po2pl,
@@ -643,11 +665,6 @@ extern "C" int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_
     pend.entries = reinterpret_cast<float4*>(scratch + off + 4 + (size_t)4 * B * rows);
     pend.item_done = reinterpret_cast<int*>(scratch + off + 4 + (size_t)4 * B * rows + (size_t)4 * B * rows * 32);
     pend.result = pend.item_done + (size_t)B * rows;
-    {
-        dim3 gb((nbh * nbw * 32 + 255) / 256, B);
-        block_range_kernel<<<gb, 256, 0, st>>>((const float4*)tgt_grid, H, W, nbh, nbw, blk);
-        DELORA_CHECK_LAUNCH("block_range_kernel");
-    }
     // persistent second kernel: enough CTAs for one wave, never more than there can be items
     const int pend_threads = kPendThreads, pend_mult = 4;     // measured flat over 128-256 threads x 4-16 CTAs per SM
     const int pend_grid = (int)std::min<long long>(((long long)B * rows * 32 + 7) / 8, (long long)pend_mult * kNumSMs);
@@ -656,6 +673,7 @@ extern "C" int delora_icp_dense_fwd_bwd(const delora_f4* src_grid, const delora_
         icp_dense_kernel<PO2PO, STATS><<<grid, kDenseThreads, 0, st>>>(                                             \
             (const float4*)src_grid, (const float4*)src_ngrid, T, (const float4*)tgt_grid, (const float4*)tgt_ngrid, \
             max_strips, g, flags, sc.rows, rows, pend);                                                             \
+        launch_block_range(st, (const float4*)tgt_grid, B, H, W, nbh, nbw, blk);                                    \
         icp_dense_pending_kernel<PO2PO, STATS><<<pend_grid, pend_threads, 0, st>>>(                                 \
             (const float4*)src_grid, (const float4*)src_ngrid, T, (const float4*)tgt_grid, (const float4*)tgt_ngrid, \
             blk, nbh, nbw, g, flags, sc.rows, rows, pend);                                                          \
