@@ -207,3 +207,24 @@ def test_bench_reference_arm_contract():
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_pipeline_staging_layout_views():
+    """`ScanPairPipeline.staging_layout` / `input_views`: one flat buffer, 256-byte aligned sections, typed views
+    that alias it (what lets a host caller ship a step with a single copy)."""
+    from delora_b200.pipeline import ScanPairPipeline
+    lay = ScanPairPipeline.staging_layout(3, 3, 1001)
+    assert lay["n_points"] % 256 == 0 and lay["transform"] % 256 == 0 and lay["bytes"] % 256 == 0
+    assert lay["n_points"] >= 2 * 3 * 3 * 1001 * 4 and lay["transform"] >= lay["n_points"] + 2 * 3 * 4
+    flat = torch.zeros((lay["bytes"],), dtype=torch.uint8)
+    points, n_points, transform = ScanPairPipeline.input_views(flat, lay)
+    assert points.shape == (6, 3, 1001) and n_points.shape == (6,) and transform.shape == (3, 12)
+    points[5, 2, 1000] = 1.5
+    n_points[5] = 77
+    transform[2, 11] = -2.0
+    raw = flat.numpy()
+    assert raw[:2 * 3 * 3 * 1001 * 4].view("float32")[-1] == 1.5
+    assert raw[lay["n_points"]:lay["n_points"] + 24].view("int32")[5] == 77
+    assert raw[lay["transform"]:lay["transform"] + 3 * 48].view("float32")[-1] == -2.0
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ScanPairPipeline(1, 16, 4, 8, (-3.0, 3.0), (-0.4, 0.1), device="cpu")
