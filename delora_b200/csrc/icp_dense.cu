@@ -13,6 +13,12 @@
 // failing lane needs.  Control flow is warp-uniform (no divergence), adjacent lanes read adjacent
 // cells (coalesced, L1-resident), and the guard is the same proof as in icp.cu: all unsearched
 // targets lie beyond a border half-plane (azimuth) or cone (elevation) of the lane's window.
+//
+// Four launches per call: icp_dense_kernel (window search, bounded number of growing steps;
+// lanes still open are appended to a work list), block_range_kernel ([min, max] range per 4 x 16-cell block of the
+// target grids, overlapped with the tail of the first kernel), icp_dense_pending_kernel (one warp per open lane:
+// range-pruned block search, float64 tie re-ranking, accumulation by the warp that completes an item) and
+// icp_finalize_kernel (icp.cu: fixed-order fp64 column sums -> losses and the 3x4 transform gradient).
 #include <stdlib.h>
 #include <algorithm>
 #include "icp_common.cuh"
