@@ -42,3 +42,16 @@ def test_sm100a_sass_present():
     from delora_b200 import build
     out = subprocess.run(["cuobjdump", "-lelf", build.build()], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_tensor_core_and_tma_instructions_in_sass():
+    """The convolution kernels really are tcgen05 + TMA code (SASS mnemonics, /opt/skills/guides/B200_PROFILING.md):
+    UTCHMMA = tcgen05.mma kind::f16, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UTMALDG = cp.async.bulk.tensor;
+    the normals kernel uses the packed fp32x2 pipe (FFMA2 / FADD2)."""
+    import re
+    import subprocess
+    from delora_b200 import build
+    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "UTMALDG", "FFMA2", "FADD2"):
+        assert re.search(r"\b" + mnemonic + r"\b", sass), mnemonic
+    assert "HMMA.16816" not in sass and "WGMMA" not in sass        # no mma.sync / wgmma fallbacks
