@@ -173,8 +173,9 @@ int delora_pack_lists(const float* pts, const float* nrm, const int32_t* n, int 
  * normal_dir        [B, src_stride] float4 out or NULL: unscaled d(pl2pl)/d(source normal)
  *                   (delora_icp_point_grads turns the two into the reference-shaped gradients)
  * scratch           fp32 [delora_icp_scratch_floats(B, src_stride)]: per-warp partial rows, column sums and
- *                   B int32 completion counters.  Zero it ONCE after allocation; every call leaves the
- *                   counters at zero again.
+ *                   B int32 completion counters (+ the dense path's range pyramid and work list).  Zero it ONCE after
+ *                   allocation; every call leaves the counters at zero again.  The layout depends on (B, src_stride):
+ *                   a buffer that is reused with a different batch size or image size must be zeroed again first.
  * The NN is the exact float64 Euclidean nearest neighbour (lowest tag on exact ties).
  */
 int     delora_icp_partial_rows(int src_stride);
