@@ -1,6 +1,7 @@
 """-m "not gpu": the oracle against the golden vectors the unmodified reference produced
 (oracle/gen_golden.py).  Bit-exact for projection / normals / point lists / pair counts; losses to
 1e-6 rel and the transform gradient to 1e-5 rel (autograd summation order is not pinned)."""
+import math
 import os
 
 import numpy as np
@@ -159,3 +160,39 @@ def test_offline_preprocessing_golden():
         normals, _, points = orc.compute_normal_vectors(img)
         assert np.array_equal(points.numpy(), z[f"points_{k}"])
         assert np.array_equal(normals.numpy(), z[f"normals_{k}"])
+
+
+def test_projection_properties_random_clouds():
+    """Oracle projection on random small clouds (no reference needed): every image pixel holds the in-FOV point of
+    minimum range that rounds to it (lowest index on ties), the survivor list is sorted by (range, index), and
+    (u, v) follow compute_2D_coordinates' op sequence."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(0, 10_000), st.integers(1, 300))
+    def check(seed, n):
+        g = torch.Generator().manual_seed(seed)
+        cloud = (torch.rand(3, n, generator=g) - 0.5) * torch.tensor([[40.0], [40.0], [6.0]])
+        cloud[:, : n // 4] = cloud[:, n // 4: 2 * (n // 4)]                       # exact duplicates: ties
+        h, w = 8, 32
+        hf, vf = [-math.pi * 179.9 / 180, math.pi * 179.9 / 180], [-0.4, 0.3]
+        image, u, v, idx, i2p = orc.project_to_img(cloud[None], h, w, hf, vf)
+        rng = torch.norm(cloud, dim=0)
+        uu = (torch.atan2(cloud[1], cloud[0]) - hf[0]) / (hf[1] - hf[0]) * (w - 1)
+        vv = (torch.atan2(cloud[2], torch.norm(cloud[:2], dim=0)) - vf[0]) / (vf[1] - vf[0]) * (h - 1)
+        ru, rv = torch.round(uu), torch.round(vv)
+        inside = (ru >= 0) & (ru <= w - 1) & (rv >= 0) & (rv <= h - 1)
+        best = {}
+        for i in range(n):
+            if inside[i]:
+                key = (int(rv[i]), int(ru[i]))
+                if key not in best or (float(rng[i]), i) < (float(rng[best[key]]), best[key]):
+                    best[key] = i
+        assert idx.shape[0] == len(best)
+        for (r, c), i in best.items():
+            assert torch.equal(image[0, :3, r, c], cloud[:, i]) and float(image[0, 3, r, c]) == float(rng[i])
+        assert int((image[0, 3] != 0).sum()) == len([i for i in best.values() if float(rng[i]) != 0.0])
+        keys = [(float(rng[i]), int(i)) for i in idx]
+        assert keys == sorted(keys) and sorted(int(i) for i in idx) == sorted(best.values())
+    import math
+    check()
