@@ -23,7 +23,6 @@ Multi-GPU: one process per GPU (torchrun), pairs sharded across ranks, no data-p
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

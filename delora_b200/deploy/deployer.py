@@ -13,7 +13,6 @@ Reference quirks kept on purpose, each behind a config key:
     -> sample j (0-based) gets weight (B - j)/B.  `plain_batch_mean: True` switches to 1/B.
   * identity pre-training compares only the LAST sample's transform with I (:324-327, :334-336).
 """
-import numpy as np
 import torch
 
 from .. import ops

@@ -2,7 +2,6 @@
 step (11.88 M fp32 = 47.5 MB for the default model), NCCL over NVLink on GPUs, gloo in the CPU
 tests.  The scan-pair kernels are rank-local; this is the only collective of the training step
 (SURVEY.md §8(e)).  One process per GPU, launched with torchrun."""
-import os
 
 import torch
 import torch.distributed as dist

@@ -1,5 +1,5 @@
 """Exploration on the GPU box: per-operator timings of the batched pipeline (not the bench)."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from delora_b200 import synthetic, _lib, ops

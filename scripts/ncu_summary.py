@@ -11,7 +11,7 @@ import csv
 import io
 import json
 import subprocess
-from collections import OrderedDict, defaultdict
+from collections import OrderedDict
 
 METRICS = [
     "gpu__time_duration.sum",

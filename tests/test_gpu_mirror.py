@@ -1,13 +1,12 @@
 """-m gpu: the reference-API mirror (same class names, signatures, return shapes as the
 reference's modules) against the oracle / golden vectors."""
-import json
 import os
 
 import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN, case_inputs, unsort_uv
+from helpers import GOLDEN, case_inputs
 from oracle import delora_oracle as orc
 
 pytestmark = pytest.mark.gpu

@@ -4,7 +4,6 @@ Bars: bit-exact for integer / index work (winner selection, index maps, lists, c
 indices, sort order); fp32 losses within 1e-5 rel of the oracle (BASELINE.json north_star);
 the 12-float transform gradient within 1e-4 of its max-abs entry; normals within a
 conditioning-aware tolerance (see test_normals)."""
-import json
 import math
 import os
 
