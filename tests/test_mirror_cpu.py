@@ -228,3 +228,35 @@ def test_pipeline_staging_layout_views():
     assert raw[lay["transform"]:lay["transform"] + 3 * 48].view("float32")[-1] == -2.0
     with pytest.raises(RuntimeError, match="CUDA"):
         ScanPairPipeline(1, 16, 4, 8, (-3.0, 3.0), (-0.4, 0.1), device="cpu")
+
+
+def test_testing_cli_config_prefers_checkpoint_parameters(tmp_path):
+    """bin/run_testing.py::build_config (reference bin/run_testing.py:19-91): YAML merge, testing identifiers,
+    checkpoint-carried network parameters, dropout off, mode / unsupervised flags."""
+    sys.path.insert(0, os.path.join(ROOT, "bin"))
+    import run_testing
+    cdir = tmp_path / "config"
+    cdir.mkdir()
+    (cdir / "config_datasets.yaml").write_text(
+        "horizontal_field_of_view: [ -179.9, 179.9 ]\n"
+        "kitti:\n  training_identifiers: [ 0 ]\n  testing_identifiers: [ 9, 10 ]\n"
+        "  vertical_field_of_view: [ -24.5, 2.0 ]\n  vertical_cells: 64\n  horizontal_cells: 720\n")
+    (cdir / "deployment_options.yaml").write_text(
+        'datasets: ["kitti"]\ndevice: "cpu"\nexperiment: "e"\ninference_only: True\nstore_dataset_in_RAM: False\n')
+    (cdir / "hyperparameters.yaml").write_text("batch_size: 4\nuse_dropout: True\nlayers: [2, 2, 2, 2]\n")
+    plain = tmp_path / "plain.pth"
+    torch.save({"model_state_dict": {}}, plain)
+    cfg = run_testing.build_config("run", "exp", str(plain), config_dir=str(cdir))
+    assert cfg["kitti"]["data_identifiers"] == [9, 10] and cfg["mode"] == "testing" and cfg["unsupervised_at_start"]
+    assert cfg["use_dropout"] is False and cfg["checkpoint"] == str(plain) and cfg["experiment"] == "exp"
+    assert cfg["kitti"]["vertical_field_of_view"][1] == pytest.approx(2.0 * np.pi / 180.0)
+    # a checkpoint that carries the training run's parameters: those win, angles are NOT converted twice
+    params = {"kitti": {"vertical_field_of_view": [-0.4, 0.03], "vertical_cells": 64, "horizontal_cells": 720,
+                        "training_identifiers": [0]},
+              "horizontal_field_of_view": [-3.14, 3.14], "layers": [1, 1, 1, 1], "use_dropout": False, "batch_size": 8}
+    rich = tmp_path / "rich.pth"
+    torch.save({"model_state_dict": {}, "parameters": params}, rich)
+    cfg = run_testing.build_config("run", "", str(rich), config_dir=str(cdir))
+    assert cfg["layers"] == [1, 1, 1, 1] and cfg["kitti"]["vertical_field_of_view"] == [-0.4, 0.03]
+    assert cfg["kitti"]["data_identifiers"] == [9, 10] and cfg["inference_only"] is True
+    assert cfg["device"] == torch.device("cpu") and cfg["store_dataset_in_RAM"] is False
