@@ -158,21 +158,29 @@ def run_reference(args):
     torch.set_num_threads(cores)
     cfg = synthetic.fov_config(h=H, w=W)
     pairs = [synthetic.make_pair(i, w_raw=W_RAW) for i in range(2)]
-    for i in range(args.warmup):
+    # Bounded sample: a pair costs ~3.5 s on the host, so the warm-up is capped at 2 pairs and the timed part at as
+    # many of the K requested steps (1 pair each) as fit into --cpu-budget-s; value = pairs / time of what ran.
+    t_w = time.perf_counter()
+    n_warm = max(1, min(args.warmup, 2))
+    for i in range(n_warm):
         cpu_reference_step(pairs[i % 2], cfg)
+    t_pair = (time.perf_counter() - t_w) / n_warm
+    n_timed = max(1, min(args.steps, int(args.cpu_budget_s / max(t_pair, 1e-3))))
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(n_timed):
         cpu_reference_step(pairs[i % 2], cfg)
     dt = time.perf_counter() - t0
-    value = args.steps / dt
+    value = n_timed / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "steps_timed": n_timed, "warmup_run": n_warm,
+        "ms_per_step": 1e3 * dt / n_timed,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1] shape: 64x2048 scan pairs, projection+normals+ICP loss fwd/bwd; "
                                "1 pair per step on the host CPU", "pairs_per_step": 1, "H": H, "W": W},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x 1 pair (oracle port of the reference CPU path, "
+                         "sample": f"{n_timed} of the {args.steps} requested steps x 1 pair, bounded by "
+                                   f"--cpu-budget-s={args.cpu_budget_s:g} (oracle port of the reference CPU path, "
                                    f"torch {torch.__version__} CPU, {cores} of {os.cpu_count()} threads = best of a sweep)"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -439,6 +447,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-pairs", type=int, default=3, help="pairs timed for the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0,
+                    help="--impl reference: wall-clock budget of the timed CPU steps (a pair costs seconds)")
     ap.add_argument("--stream-frames", type=int, default=200,
                     help="frames of the informational streaming-inference leg (0 = skip)")
     ap.add_argument("--train-steps", type=int, default=5, help="steps of the informational full-training-step leg (0 = skip)")
