@@ -195,6 +195,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # NCCL's own log lines (e.g. "NCCL version ...") go to stderr: stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=device)
     from delora_b200 import synthetic
     from delora_b200.pipeline import ScanPairPipeline
