@@ -1,0 +1,388 @@
+// Encoder convolutions, second-generation kernel (round 2): row-block implicit GEMM with the filter taps issued from
+// ONE halo tile in shared memory.
+//
+// Same operator as conv_tc.cu (the reference's nn.Conv2d layers, src/models/resnet_modified.py:126-134 used at
+// :159-177; circular padding in W, zero padding in H, materialised in the padded NHWC bf16 layout) for the layers
+// that carry the FLOPs: 3x3 (and 1x1) stride-1 convolutions with Cout % 128 == 0, and the data gradient of the
+// strided 3x3 convolutions by PHASE DECOMPOSITION (each output phase (h % sh, w % sw) is a small convolution of the
+// un-upsampled output gradient with a subset of the flipped taps: no zero-upsampled tensor, no MMAs on zeros).
+//
+// Why a second kernel: conv_tc.cu loads every (tap, 64-channel chunk) as its own TMA box, so an activation tile is
+// fetched 9x from L2 and a 128 x 64 tile only buys 128 tensor cycles per 24 KB of shared-memory fill; profiles/
+// r01_conv_tcgen05.md shows 4.0x DRAM over-read and 15-60 % tensor-pipe utilisation.  Here
+//   * GEMM roles are swapped: M = 128 OUTPUT CHANNELS (A operand = filter tile [128 co][64 ci], K-major), N = the NS
+//     pixels of one output-row segment (B operand = activation rows, K-major), so a job's accumulators are R rows x
+//     NS pixels = <= 256 TMEM columns and ANY image width maps onto the N dimension (multiples of 16);
+//   * per job and 64-channel chunk ONE TMA box brings the (R + 2) x (NS + 2) pixel halo tile; the B descriptor of
+//     tap (r, q), row i starts at byte ((i + r) * (NS + 2) + q) * 128 of that tile -- the tensor core applies the
+//     128-byte swizzle on absolute shared-memory addresses, so 128-byte-granular start offsets need no re-layout
+//     (measured: scripts/umma_probe.cu, profiles/r02_umma_probe.log).  Activation traffic per MMA drops ~6x;
+//   * CTAs are persistent (grid = min(jobs, SMs)), TMEM is allocated once (512 columns = two accumulator sets): the
+//     epilogue of job j overlaps the MMAs of job j + 1; separate producer warps stream halo tiles (2 stages) and
+//     filter tiles (4-6 stages);
+//   * epilogue: tcgen05.ld gives a thread one channel x 32 pixels; a 32 x 32 transpose through shared memory turns
+//     that into one pixel x 32 channels (64 contiguous bytes of NHWC), then residual / activation / act' / store as
+//     in conv_tc.cu.
+// Warp roles: 0 halo-tile producer, 1 filter producer, 2 MMA issuer + TMEM owner, 3..6 epilogue.
+#include <string.h>
+#include <stdlib.h>
+#include "tc_common.cuh"
+
+namespace delora {
+
+constexpr int kRowsThreads = 224;
+constexpr int kRowsMaxTaps = 9;
+constexpr int kRowsMaxPhases = 4;
+constexpr int kWTileBytes = 128 * 64 * 2;          // filter tile: 128 output channels x 64 input channels
+
+struct RowsPhase {
+    int ntaps;
+    int oh, ow;                                    // output pixel = (out_sh * h + oh, out_sw * w + ow)
+    signed char drow[kRowsMaxTaps], dcol[kRowsMaxTaps], wtap[kRowsMaxTaps];
+};
+
+struct RowsParams {
+    int B, Cin, Cout;
+    int Hout, Wout;                                // output tensor (unpadded) size
+    int Hg, Wg;                                    // job grid extent in phase coordinates (= Hout, Wout for stride 1)
+    int out_sh, out_sw;
+    int NS, R;                                     // pixels per row segment (MMA N), rows per job; R * NS <= 256
+    int segs_w, blocks_h, co_tiles, kchunks;
+    int n_phases;
+    int n_jobs;
+    int act;
+    int w_stages;
+    int a_stage_bytes;
+    RowsPhase phase[kRowsMaxPhases];
+};
+
+struct RowsJob { int ct, ph, b, h0, w0; };
+
+__device__ __forceinline__ RowsJob rows_decode(const RowsParams& p, int job) {
+    RowsJob j;
+    j.ct = job % p.co_tiles; job /= p.co_tiles;
+    j.w0 = (job % p.segs_w) * p.NS; job /= p.segs_w;
+    j.h0 = (job % p.blocks_h) * p.R; job /= p.blocks_h;
+    j.b = job % p.B; job /= p.B;
+    j.ph = job;                                    // phase-major: the phases with the most taps come first (host order)
+    return j;
+}
+
+__global__ void __launch_bounds__(kRowsThreads, 1)
+conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                    const __nv_bfloat16* __restrict__ residual, const __nv_bfloat16* __restrict__ saved,
+                    __nv_bfloat16* __restrict__ y, const __grid_constant__ RowsParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;                                        // 2 halo-tile stages
+    uint8_t* smem_w = smem_a + 2 * p.a_stage_bytes;                // filter ring
+    float* stage = reinterpret_cast<float*>(smem_w + p.w_stages * kWTileBytes);   // 4 x 4 KB transpose buffers
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage) + 4 * 4096);
+    uint64_t* a_empty = a_full + 2;
+    uint64_t* acc_full = a_empty + 2;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* w_full = acc_empty + 2;
+    uint64_t* w_empty = w_full + 8;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_empty + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.w_stages;
+    const int pitch = p.NS + 2;                                    // pixels per halo-tile row
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1);
+            mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4);
+        }
+        for (int s = 0; s < S; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr_smem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================== halo-tile producer =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&map_x);
+            const uint32_t a_bytes = (uint32_t)(pitch * (p.R + 2) * 128);
+            uint32_t it = 0;
+            for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x) {
+                const RowsJob j = rows_decode(p, job);
+                for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+                    const uint32_t s = it & 1;
+                    mbar_wait(a_empty + s, ((it >> 1) & 1) ^ 1);
+                    mbar_expect_tx(a_full + s, a_bytes);
+                    // local (row j, pixel c) = padded input pixel (h0 + j, w0 + c)
+                    tma_load_4d(smem_a + s * p.a_stage_bytes, &map_x, a_full + s, kc * 64, j.w0, j.h0, j.b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== filter producer =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&map_w);
+            uint32_t it = 0;
+            for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x) {
+                const RowsJob j = rows_decode(p, job);
+                const RowsPhase& ph = p.phase[j.ph];
+                for (int kc = 0; kc < p.kchunks; ++kc)
+                    for (int t = 0; t < ph.ntaps; ++t, ++it) {
+                        const uint32_t s = it % S;
+                        mbar_wait(w_empty + s, ((it / S) & 1) ^ 1);
+                        mbar_expect_tx(w_full + s, kWTileBytes);
+                        tma_load_2d(smem_w + s * kWTileBytes, &map_w, w_full + s, (int)ph.wtap[t] * p.Cin + kc * 64,
+                                    j.ct * 128);
+                    }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, p.NS, 0, 0);
+            uint32_t a_it = 0, w_it = 0, j_it = 0;
+            for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, ++j_it) {
+                const RowsJob j = rows_decode(p, job);
+                const RowsPhase& ph = p.phase[j.ph];
+                const uint32_t ab = j_it & 1;
+                mbar_wait(acc_empty + ab, ((j_it >> 1) & 1) ^ 1);          // epilogue drained this accumulator set
+                tc_fence_after();
+                const uint32_t acc = tmem_base + ab * 256;
+                for (int kc = 0; kc < p.kchunks; ++kc, ++a_it) {
+                    const uint32_t as = a_it & 1;
+                    mbar_wait(a_full + as, (a_it >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem_a + as * p.a_stage_bytes);
+                    for (int t = 0; t < ph.ntaps; ++t, ++w_it) {
+                        const uint32_t ws = w_it % S;
+                        mbar_wait(w_full + ws, (w_it / S) & 1);
+                        tc_fence_after();
+                        const uint64_t dw = make_smem_desc(smem_u32(smem_w + ws * kWTileBytes));
+                        const uint32_t tap_off = (uint32_t)(((int)ph.drow[t] * pitch + (int)ph.dcol[t]) * 128);
+                        const uint32_t first = (kc == 0 && t == 0) ? 0u : 1u;
+                        for (int i = 0; i < p.R; ++i) {
+                            const uint64_t dx = make_smem_desc(a_base + tap_off + (uint32_t)(i * pitch * 128));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)          // 64 channels = 4 x K16; +32 bytes = +2 in 16-byte units
+                                tcgen05_mma_bf16(acc + (uint32_t)(i * p.NS), dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2),
+                                                 idesc, (k > 0) ? 1u : first);
+                        }
+                        tcgen05_commit(w_empty + ws);            // filter stage free when these MMAs retire
+                    }
+                    tcgen05_commit(a_empty + as);                // halo tile free
+                }
+                tcgen05_commit(acc_full + ab);                   // accumulators of this job complete
+            }
+        }
+    } else {
+        // ===================== epilogue warps 3..6 =====================
+        const int quarter = warp & 3;                            // TMEM lanes 32*quarter .. +31 = output channels
+        float* st = stage + quarter * 1024;
+        const int Wp = p.Wout + 2, Hp = p.Hout + 2;
+        const int n_blocks = (p.R * p.NS) >> 5;
+        uint32_t j_it = 0;
+        for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, ++j_it) {
+            const RowsJob j = rows_decode(p, job);
+            const RowsPhase& ph = p.phase[j.ph];
+            const uint32_t ab = j_it & 1;
+            mbar_wait(acc_full + ab, (j_it >> 1) & 1);
+            tc_fence_after();
+            const int c_first = j.ct * 128 + quarter * 32;
+            for (int cb = 0; cb < n_blocks; ++cb) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * 256 + (uint32_t)(cb * 32), acc);
+                // transpose: thread = channel `lane` holds 32 pixels -> thread = pixel `lane` holds 32 channels.
+                // XOR-swizzled 32 x 32 fp32 tile: both directions are bank-conflict free
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) st[jj * 32 + (lane ^ jj)] = __uint_as_float(acc[jj]);
+                __syncwarp();
+                float v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = st[lane * 32 + (c ^ lane)];
+                __syncwarp();
+                const int col = cb * 32 + lane;
+                const int i = col / p.NS, wl = col - i * p.NS;
+                const int hg = j.h0 + i, wg = j.w0 + wl;
+                const int ho = hg * p.out_sh + ph.oh, wo = wg * p.out_sw + ph.ow;
+                if (hg < p.Hg && wg < p.Wg && ho < p.Hout && wo < p.Wout) {
+                    const size_t pix = ((size_t)j.b * Hp + (ho + 1)) * Wp + (wo + 1);
+                    epilogue_store32(v, residual, saved, y, pix * p.Cout + c_first, p.act, wo == 0, wo == p.Wout - 1,
+                                     (size_t)p.Wout * p.Cout);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + ab);
+        }
+    }
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------- host side
+static int rows_encode_maps(CUtensorMap* mx, CUtensorMap* mw, const void* x, const void* w, int B, int Hin, int Win,
+                            int Cin, int Cout, int wtaps, int NS, int R) {
+    PFN_cuTensorMapEncodeTiled_v12000 encode = get_tensor_map_encoder();
+    if (!encode) return 1;
+    const int Hp = Hin + 2, Wp = Win + 2;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Wp * Cin * 2, (cuuint64_t)Hp * Wp * Cin * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(NS + 2), (cuuint32_t)(R + 2), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (encode(mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 2;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)wtaps * Cin, (cuuint64_t)Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)wtaps * Cin * 2};
+        cuuint32_t box[2] = {64, 128};
+        cuuint32_t estr[2] = {1, 1};
+        if (encode(mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 3;
+    }
+    return 0;
+}
+
+// Tensor maps depend only on (pointers, shapes); the encoder's activations, filters and gradients live in
+// persistent buffers, so a small per-thread cache removes the encode cost from the 40 launches of a step.
+struct RowsMapKey { const void* x; const void* w; int B, Hin, Win, Cin, Cout, wtaps, NS, R; };
+struct RowsMapEntry { RowsMapKey k; CUtensorMap mx, mw; };
+
+static const RowsMapEntry* rows_get_maps(const RowsMapKey& key) {
+    static thread_local RowsMapEntry cache[128];
+    static thread_local int used = 0, next = 0;
+    for (int i = 0; i < used; ++i) {
+        const RowsMapKey& c = cache[i].k;
+        if (c.x == key.x && c.w == key.w && c.B == key.B && c.Hin == key.Hin && c.Win == key.Win && c.Cin == key.Cin &&
+            c.Cout == key.Cout && c.wtaps == key.wtaps && c.NS == key.NS && c.R == key.R)
+            return &cache[i];
+    }
+    RowsMapEntry& e = cache[next];
+    if (rows_encode_maps(&e.mx, &e.mw, key.x, key.w, key.B, key.Hin, key.Win, key.Cin, key.Cout, key.wtaps, key.NS,
+                         key.R) != 0)
+        return nullptr;
+    e.k = key;
+    const RowsMapEntry* out = &e;
+    next = (next + 1) % 128;
+    if (used < 128) ++used;
+    return out;
+}
+
+// segment width / rows per job for a job grid of Hg x Wg positions: NS = multiple of 16 covering the row in equal
+// segments of at most 128 pixels; R rows so that R * NS <= 256 accumulator columns (a multiple of 32)
+static void rows_pick_tile(int Hg, int Wg, int* NS, int* R) {
+    const int segs = (Wg + 127) / 128;
+    int ns = ((Wg + segs - 1) / segs + 15) / 16 * 16;
+    if (ns < 16) ns = 16;
+    int r = 256 / ns;
+    if ((r * ns) % 32 != 0) r -= 1;
+    if (r > Hg) r = Hg;
+    if (r < 1) r = 1;
+    while ((r * ns) % 32 != 0) ++r;                 // r = 1 with ns % 32 == 16: take two rows (second one masked)
+    *NS = ns; *R = r;
+}
+
+bool conv_rows_eligible(int Cin, int Cout, int ksize) {
+    return Cin % 64 == 0 && Cout % 128 == 0 && (ksize == 3 || ksize == 1);
+}
+
+// stride-1 convolution (up_h = up_w = 1) or data gradient of a stride-(up_h, up_w) 3x3 convolution (x = output
+// gradient of that convolution, w = its flipped / transposed filter [Cout][9][Cin], y = input gradient Hout x Wout)
+int conv_rows_launch(const void* x, const void* w, const void* residual, const void* saved, void* y, int B, int Hout,
+                     int Wout, int Cin, int Cout, int ksize, int up_h, int up_w, int act, cudaStream_t stream) {
+    RowsParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.Cin = Cin; p.Cout = Cout; p.Hout = Hout; p.Wout = Wout; p.act = act;
+    p.out_sh = up_h; p.out_sw = up_w;
+    p.Hg = (Hout + up_h - 1) / up_h; p.Wg = (Wout + up_w - 1) / up_w;
+    const int Hin = (Hout - 1) / up_h + 1, Win = (Wout - 1) / up_w + 1;      // size of x (unpadded)
+    if (ksize == 1) {
+        p.n_phases = 1;
+        p.phase[0].ntaps = 1; p.phase[0].drow[0] = 1; p.phase[0].dcol[0] = 1; p.phase[0].wtap[0] = 0;
+    } else if (up_h == 1 && up_w == 1) {
+        p.n_phases = 1;
+        p.phase[0].ntaps = 9;
+        for (int t = 0; t < 9; ++t) { p.phase[0].drow[t] = (signed char)(t / 3); p.phase[0].dcol[t] = (signed char)(t % 3); p.phase[0].wtap[t] = (signed char)t; }
+    } else {
+        // out[h][w] = sum_{r', q'} U[h + r' - 1][w + q' - 1] * Wf[r'][q'],  U = zero-upsampled x: only taps with
+        // (h + r' - 1) % up_h == 0 and (w + q' - 1) % up_w == 0 contribute.  Phase (fh, fw): h = up_h * jh + fh.
+        // Local halo-tile coordinates: padded x row jh0 + drow, drow = (fh + r' - 1) / up_h + 1 (same for columns).
+        int np = 0;
+        // phases ordered by decreasing tap count (static round-robin over CTAs: expensive jobs first)
+        for (int pass = 9; pass >= 1; --pass)
+            for (int fh = 0; fh < up_h; ++fh)
+                for (int fw = 0; fw < up_w; ++fw) {
+                    RowsPhase ph;
+                    memset(&ph, 0, sizeof(ph));
+                    ph.oh = fh; ph.ow = fw;
+                    for (int r = 0; r < 3; ++r) {
+                        if ((fh + r - 1 + up_h) % up_h != 0) continue;
+                        for (int q = 0; q < 3; ++q) {
+                            if ((fw + q - 1 + up_w) % up_w != 0) continue;
+                            // floor division of (fh + r - 1) by up_h, values -1 .. 2
+                            const int dr = (fh + r - 1 + up_h) / up_h - 1, dq = (fw + q - 1 + up_w) / up_w - 1;
+                            ph.drow[ph.ntaps] = (signed char)(dr + 1); ph.dcol[ph.ntaps] = (signed char)(dq + 1);
+                            ph.wtap[ph.ntaps] = (signed char)(r * 3 + q);
+                            ++ph.ntaps;
+                        }
+                    }
+                    if (ph.ntaps == pass) p.phase[np++] = ph;
+                }
+        p.n_phases = np;
+    }
+    rows_pick_tile(p.Hg, p.Wg, &p.NS, &p.R);
+    p.segs_w = (p.Wg + p.NS - 1) / p.NS;
+    p.blocks_h = (p.Hg + p.R - 1) / p.R;
+    p.co_tiles = Cout / 128;
+    p.kchunks = Cin / 64;
+    p.n_jobs = p.n_phases * B * p.blocks_h * p.segs_w * p.co_tiles;
+    p.a_stage_bytes = (((p.NS + 2) * (p.R + 2) * 128) + 1023) / 1024 * 1024;
+    const int fixed = 2 * p.a_stage_bytes + 4 * 4096 + 256 + 1024;
+    int ws = (227 * 1024 - fixed) / kWTileBytes;
+    if (ws > 8) ws = 8;
+    DELORA_CHECK_ARG(ws >= 2, "conv_rows: tile %dx%d leaves no room for the filter ring", p.NS, p.R);
+    p.w_stages = ws;
+    const RowsMapKey key = {x, w, B, Hin, Win, Cin, Cout, ksize * ksize, p.NS, p.R};
+    const RowsMapEntry* maps = rows_get_maps(key);
+    DELORA_CHECK_ARG(maps != nullptr, "conv_rows: cuTensorMapEncodeTiled failed or is unavailable");
+    const size_t smem = (size_t)fixed + (size_t)ws * kWTileBytes;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {};
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        DELORA_CHECK_ARG(e == cudaSuccess, "conv_rows: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    const int grid = p.n_jobs < kNumSMs ? p.n_jobs : kNumSMs;
+    conv_rows_tc_kernel<<<grid, kRowsThreads, smem, stream>>>(maps->mx, maps->mw, (const __nv_bfloat16*)residual,
+                                                               (const __nv_bfloat16*)saved, (__nv_bfloat16*)y, p);
+    DELORA_CHECK_LAUNCH("conv_rows_tc_kernel");
+    return 0;
+}
+
+}  // namespace delora
+
+using namespace delora;
+
+extern "C" int delora_conv2d_dgrad_bf16(const void* dz, const void* w_flip, const void* residual, const void* saved,
+                                        void* dx, int B, int Hin, int Win, int Cin, int Cout, int stride_h, int stride_w,
+                                        int act, void* stream) {
+    // Cin / Cout are those of the FORWARD convolution: dz has Cout channels, dx has Cin channels
+    DELORA_CHECK_ARG(dz && w_flip && dx, "delora_conv2d_dgrad_bf16: null pointer");
+    DELORA_CHECK_ARG(act >= 0 && act <= 4 && (act < 3 || saved), "delora_conv2d_dgrad_bf16: act=%d (3/4 need `saved`)", act);
+    DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin >= 1 && Win >= 1,
+                     "delora_conv2d_dgrad_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
+    DELORA_CHECK_ARG(stride_w == 1 || Win % 2 == 0, "delora_conv2d_dgrad_bf16: stride_w = 2 needs an even Win (got %d)", Win);
+    DELORA_CHECK_ARG(conv_rows_eligible(Cout, Cin, 3),
+                     "delora_conv2d_dgrad_bf16: needs Cin %% 128 == 0 and Cout %% 64 == 0 (got Cin=%d, Cout=%d)", Cin, Cout);
+    return conv_rows_launch(dz, w_flip, residual, saved, dx, B, Hin, Win, Cout, Cin, 3, stride_h, stride_w, act,
+                            (cudaStream_t)stream);
+}

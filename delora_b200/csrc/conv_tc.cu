@@ -20,10 +20,8 @@
 // tcgen05.ld, add the residual, apply the activation, convert to bf16 and store NHWC (plus the
 // circular halo columns).  Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM allocator,
 // 2..5 = epilogue.
-#include <cuda.h>
-#include <cuda_bf16.h>
-#include <cudaTypedefs.h>
-#include "common.cuh"
+#include <stdlib.h>
+#include "tc_common.cuh"
 
 namespace delora {
 
@@ -44,83 +42,6 @@ struct ConvParams {
     int act;                          // 0 none, 1 relu, 2 tanh
     int stages;                       // smem ring depth (<= kMaxStages)
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                            int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                                 uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start address >> 4 | LBO (unused for swizzled K-major) = 1 | SBO = 1024 B (8 rows x 128 B) | version 1 |
-// layout_type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-    if (act == 1) return fmaxf(v, 0.0f);
-    if (act == 2) {           // MUFU.TANH: 2^-11 relative error, far below the bf16 output rounding
-        float t;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v));
-        return t;
-    }
-    return v;
-}
 
 // ---------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(kConvThreads, 2)
@@ -726,17 +647,7 @@ weight_prep_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Ci
 }
 
 // ---------------------------------------------------------------- host side
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
-    }
-    return fn;
-}
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() { return get_tensor_map_encoder(); }
 
 struct TensorMaps {
     CUtensorMap x, w;
@@ -805,7 +716,25 @@ static const TensorMaps* get_maps(const void* x, const void* w, int B, int Hin, 
 
 }  // namespace delora
 
+namespace delora {
+bool conv_rows_eligible(int Cin, int Cout, int ksize);
+int conv_rows_launch(const void* x, const void* w, const void* residual, const void* saved, void* y, int B, int Hout,
+                     int Wout, int Cin, int Cout, int ksize, int up_h, int up_w, int act, cudaStream_t stream);
+// DELORA_CONV_ROWS=0 keeps every convolution on the first-generation kernel (A/B measurements)
+static int g_conv_rows = -1;
+static bool use_conv_rows() {
+    if (g_conv_rows < 0) { const char* e = getenv("DELORA_CONV_ROWS"); g_conv_rows = (e && e[0] == '0') ? 0 : 1; }
+    return g_conv_rows == 1;
+}
+}  // namespace delora
+
 using namespace delora;
+
+extern "C" int delora_conv_select_kernel(int rows_kernel) {
+    const int prev = use_conv_rows() ? 1 : 0;
+    if (rows_kernel == 0 || rows_kernel == 1) g_conv_rows = rows_kernel;
+    return prev;
+}
 
 extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void* residual, const void* saved, void* y,
                                         int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride_h,
@@ -817,6 +746,8 @@ extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void
                      Cin, Cout);
     DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin >= 1 && Win >= 1,
                      "delora_conv2d_fprop_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
+    if (stride_h == 1 && stride_w == 1 && conv_rows_eligible(Cin, Cout, ksize) && use_conv_rows())
+        return conv_rows_launch(x, w, residual, saved, y, B, Hin, Win, Cin, Cout, ksize, 1, 1, act, (cudaStream_t)stream);
     ConvParams p;
     p.B = B; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
     p.stride_h = stride_h; p.stride_w = stride_w; p.pad_off = (ksize == 1) ? 1 : 0; p.act = act;

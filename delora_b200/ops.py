@@ -296,6 +296,26 @@ def conv2d_fprop(x, weight, hin, win, ksize, stride, act=ACT_NONE, residual=None
     return out
 
 
+def conv2d_dgrad_eligible(cin, cout, win, stride):
+    """Can delora_conv2d_dgrad_bf16 (phase-decomposed data gradient) take this layer?"""
+    return cin % 128 == 0 and cout % 64 == 0 and (stride[1] == 1 or win % 2 == 0)
+
+
+def conv2d_dgrad(dz, w_flip, hin, win, stride, act=ACT_NONE, residual=None, out=None, saved=None):
+    """dz [B,Hout+2,Wout+2,Cout], w_flip [Cin,9,Cout] -> dx [B,Hin+2,Win+2,Cin] (3x3 conv of `stride`)."""
+    b, _, _, cout = dz.shape
+    cin = w_flip.shape[0]
+    if out is None:
+        out = padded_nhwc_zeros(b, hin, win, cin, dz.device)
+    L = _lib.lib()
+    _lib.check(L.delora_conv2d_dgrad_bf16(_req(dz, torch.bfloat16, "dz"), _req(w_flip, torch.bfloat16, "w_flip"),
+                                          _req(residual, torch.bfloat16, "residual") if residual is not None else None,
+                                          _req(saved, torch.bfloat16, "saved") if saved is not None else None,
+                                          out.data_ptr(), b, hin, win, cin, cout, stride[0], stride[1], int(act),
+                                          _stream()), "delora_conv2d_dgrad_bf16")
+    return out
+
+
 _wgrad_scratch = {}
 
 

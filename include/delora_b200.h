@@ -243,6 +243,21 @@ int delora_icp_point_grads(const delora_f4* point_dir, const delora_f4* normal_d
 int delora_conv2d_fprop_bf16(const void* x, const void* w, const void* residual, const void* saved, void* y, int B,
                              int Hin, int Win, int Cin, int Cout, int ksize, int stride_h, int stride_w, int act,
                              void* stream);
+/* Measurement switch: 1 (default) lets delora_conv2d_fprop_bf16 use the row-block kernel (csrc/conv_rows.cu) for
+ * stride-1 layers with Cout % 128 == 0, 0 keeps every layer on the tap-per-TMA kernel (csrc/conv_tc.cu); any other
+ * value only queries.  Returns the previous setting.  Same effect as the environment variable DELORA_CONV_ROWS=0. */
+int delora_conv_select_kernel(int rows_kernel);
+/* Data gradient of a 3x3 convolution of stride (stride_h, stride_w) in {1,2}^2 -- autograd's backward of the same
+ * nn.Conv2d layers (src/models/resnet_modified.py:126-134) w.r.t. their input -- by PHASE DECOMPOSITION: every
+ * output phase (h % stride_h, w % stride_w) is a small convolution of the (un-upsampled) output gradient with the
+ * subset of flipped taps that hits non-zero positions; no zero-upsampled tensor is materialised.
+ * dz [B,Hout+2,Wout+2,Cout] (Hout = (Hin-1)/stride_h + 1 ...), w_flip [Cin, 9, Cout] (delora_conv_weight_prep_bf16),
+ * residual / saved / dx [B,Hin+2,Win+2,Cin]; act as in delora_conv2d_fprop_bf16 (3 / 4 = multiply by act'(saved)).
+ * Needs Cin % 128 == 0, Cout % 64 == 0 and, for stride_w = 2, an even Win (an odd circular width mixes the phases at
+ * the seam: use delora_zero_upsample_nhwc_bf16 + delora_conv2d_fprop_bf16 there). */
+int delora_conv2d_dgrad_bf16(const void* dz, const void* w_flip, const void* residual, const void* saved, void* dx,
+                             int B, int Hin, int Win, int Cin, int Cout, int stride_h, int stride_w, int act,
+                             void* stream);
 /* Weight gradient of the same convolution on tcgen05 (split-K over pixels, deterministic reduction):
  * x [B,Hin+2,Win+2,Cin] padded NHWC bf16 (the layer input), dz [B,Hout+2,Wout+2,Cout] padded NHWC bf16
  * (gradient w.r.t. the pre-activation output) -> dw [Cout, Cin_true, k, k] fp32 (torch layout; Cin_true <= Cin

@@ -1,0 +1,126 @@
+"""Development check of the row-block convolution kernel (csrc/conv_rows.cu) on a B200:
+new kernel vs the first-generation kernel (csrc/conv_tc.cu) on identical inputs, plus CUDA-event timings.
+Usage: python scripts/gpu_conv_rows_check.py [quick]"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from delora_b200 import _lib, ops  # noqa: E402
+
+DEV = "cuda"
+L = _lib.lib()
+
+
+def rand_padded(b, h, w, c, gen, scale=0.5):
+    x = ops.padded_nhwc_zeros(b, h, w, c, DEV)
+    x[:, 1:h + 1, 1:w + 1] = (torch.randn(b, h, w, c, device=DEV, generator=gen) * scale).to(torch.bfloat16)
+    x[:, 1:h + 1, 0] = x[:, 1:h + 1, w]
+    x[:, 1:h + 1, w + 1] = x[:, 1:h + 1, 1]
+    return x
+
+
+def timed(fn, iters=10):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def check_fprop(b, cin, cout, h, w, k, act, use_res, time_it=True):
+    gen = torch.Generator(device=DEV).manual_seed(cin + cout + h + w)
+    x = rand_padded(b, h, w, cin, gen)
+    wt = (torch.randn(cout, k * k, cin, device=DEV, generator=gen) / (cin * k * k) ** 0.5).to(torch.bfloat16)
+    res = rand_padded(b, h, w, cout, gen) if use_res else None
+    saved = rand_padded(b, h, w, cout, gen, 0.3) if act >= 3 else None
+    L.delora_conv_select_kernel(0)
+    y_old = ops.conv2d_fprop(x, wt, h, w, k, (1, 1), act, res, saved=saved)
+    L.delora_conv_select_kernel(1)
+    y_new = ops.conv2d_fprop(x, wt, h, w, k, (1, 1), act, res, saved=saved)
+    torch.cuda.synchronize()
+    d = (y_new.float() - y_old.float()).abs()
+    ref = y_old.float().abs().max().item()
+    bad = (d > 2e-2 * max(1.0, ref)).sum().item()
+    msg = f"fprop B{b} {cin}->{cout} {h}x{w} k{k} act{act} res{int(use_res)}: maxdiff {d.max().item():.4g} (ref max {ref:.3g}) bad {bad}"
+    if time_it:
+        out = ops.padded_nhwc_zeros(b, h, w, cout, DEV)
+        L.delora_conv_select_kernel(0)
+        t_old = timed(lambda: ops.conv2d_fprop(x, wt, h, w, k, (1, 1), act, res, out, saved))
+        L.delora_conv_select_kernel(1)
+        t_new = timed(lambda: ops.conv2d_fprop(x, wt, h, w, k, (1, 1), act, res, out, saved))
+        fl = 2.0 * b * h * w * cout * cin * k * k
+        msg += f" | old {t_old * 1e3:.1f} us ({fl / t_old / 1e9:.0f} TF/s)  new {t_new * 1e3:.1f} us ({fl / t_new / 1e9:.0f} TF/s)"
+    print(("OK   " if bad == 0 else "FAIL ") + msg, flush=True)
+    return bad == 0
+
+
+def check_dgrad(b, cin, cout, h, w, stride, act, use_res, time_it=True):
+    """cin/cout/h/w of the FORWARD conv (input h x w, cin channels)."""
+    gen = torch.Generator(device=DEV).manual_seed(cin + cout + h + w + 1)
+    ho, wo = ops.conv_out_size(h, stride[0]), ops.conv_out_size(w, stride[1])
+    dz = rand_padded(b, ho, wo, cout, gen)
+    wf = (torch.randn(cin, 9, cout, device=DEV, generator=gen) / (cout * 9) ** 0.5).to(torch.bfloat16)
+    res = rand_padded(b, h, w, cin, gen) if use_res else None
+    saved = rand_padded(b, h, w, cin, gen, 0.3) if act >= 3 else None
+    L.delora_conv_select_kernel(0)
+
+    def old(out=None):
+        src = dz if stride == (1, 1) else ops.zero_upsample(dz, ho, wo, stride, None, (h, w))
+        return ops.conv2d_fprop(src, wf, h, w, 3, (1, 1), act, res, out, saved)
+    y_old = old()
+    y_new = ops.conv2d_dgrad(dz, wf, h, w, stride, act, res, None, saved)
+    torch.cuda.synchronize()
+    d = (y_new.float() - y_old.float()).abs()
+    ref = y_old.float().abs().max().item()
+    bad = (d > 2e-2 * max(1.0, ref)).sum().item()
+    msg = f"dgrad B{b} fwd {cin}->{cout} in {h}x{w} s{stride} act{act} res{int(use_res)}: maxdiff {d.max().item():.4g} (ref max {ref:.3g}) bad {bad}"
+    if time_it:
+        out = ops.padded_nhwc_zeros(b, h, w, cin, DEV)
+        t_old = timed(lambda: old(out))
+        t_new = timed(lambda: ops.conv2d_dgrad(dz, wf, h, w, stride, act, res, out, saved))
+        fl = 2.0 * b * ho * wo * cout * cin * 9
+        msg += f" | old {t_old * 1e3:.1f} us  new {t_new * 1e3:.1f} us ({fl / t_new / 1e9:.0f} TF/s useful)"
+    L.delora_conv_select_kernel(1)
+    print(("OK   " if bad == 0 else "FAIL ") + msg, flush=True)
+    return bad == 0
+
+
+def main():
+    quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+    ok = True
+    t0 = time.time()
+    # small correctness cases first (ragged widths / heights, 1x1, both activations, backward epilogues)
+    ok &= check_fprop(1, 64, 128, 8, 128, 3, 0, False, False)
+    ok &= check_fprop(2, 128, 128, 16, 128, 3, 1, True, False)
+    ok &= check_fprop(1, 128, 256, 7, 90, 3, 2, True, False)
+    ok &= check_fprop(1, 256, 256, 5, 45, 3, 3, True, False)
+    ok &= check_fprop(2, 512, 512, 32, 23, 3, 4, False, False)
+    ok &= check_fprop(1, 512, 512, 32, 64, 3, 2, True, False)
+    ok &= check_fprop(1, 256, 128, 9, 200, 1, 0, False, False)
+    ok &= check_dgrad(1, 128, 256, 8, 128, (1, 2), 3, True, False)
+    ok &= check_dgrad(1, 256, 512, 16, 64, (2, 2), 3, True, False)
+    ok &= check_dgrad(1, 256, 512, 15, 46, (2, 2), 0, False, False)
+    ok &= check_dgrad(1, 128, 128, 8, 96, (1, 1), 4, True, False)
+    print(f"-- small cases done in {time.time() - t0:.1f} s, ok={ok}", flush=True)
+    if not quick:
+        # bench shapes (B = 16, 64x2048 image): L2 128ch @64x256, L3 256ch @64x128, L4 512ch @32x64
+        check_fprop(16, 128, 128, 64, 256, 3, 2, True)
+        check_fprop(16, 256, 256, 64, 128, 3, 2, True)
+        check_fprop(16, 512, 512, 32, 64, 3, 2, True)
+        check_fprop(16, 128, 128, 64, 256, 3, 3, True)
+        check_dgrad(16, 128, 256, 64, 256, (1, 2), 3, True)
+        check_dgrad(16, 256, 512, 64, 128, (2, 2), 3, True)
+    print("ALL OK" if ok else "SOME FAILED", flush=True)
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
