@@ -58,22 +58,31 @@ struct RowsParams {
 
 struct RowsJob { int ct, ph, b, h0, w0; };
 
-__device__ __forceinline__ RowsJob rows_decode(const RowsParams& p, int job) {
+// job -> (co tile, phase, image, first row, first column).  With CTA pairs (CG = 2) a job covers 2R rows (rank r takes
+// rows h0 + r R .. + R - 1) and 256 output channels (rank r takes channels (2 ct + r) * 128 .. + 127).
+__device__ __forceinline__ RowsJob rows_decode(const RowsParams& p, int job, int cg) {
     RowsJob j;
     j.ct = job % p.co_tiles; job /= p.co_tiles;
     j.w0 = (job % p.segs_w) * p.NS; job /= p.segs_w;
-    j.h0 = (job % p.blocks_h) * p.R; job /= p.blocks_h;
+    j.h0 = (job % p.blocks_h) * p.R * cg; job /= p.blocks_h;
     j.b = job % p.B; job /= p.B;
     j.ph = job;                                    // phase-major: the phases with the most taps come first (host order)
     return j;
 }
 
+// CG = 1: one CTA per job, tcgen05.mma.cta_group::1 with M = 128 output channels, N = NS pixels.
+// CG = 2: a CTA PAIR per job (cluster of 2, one per SM of a TPC), tcgen05.mma.cta_group::2 with M = 256 output
+//         channels (128 per CTA: each CTA loads its own filter tile) and N = 2 NS pixels (each CTA loads the halo
+//         tile of its own R rows): per SM the MMA reads 64 instead of 128 B/clk of shared memory and each filter
+//         byte is fetched for twice the pixels -- measured necessary: the shared-memory port (128 B/clk, MMA operand
+//         reads + TMA fills) is what bounds these kernels (scripts/umma_probe2.cu, profiles/r02_umma_probe2.log).
+template <int CG>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __nv_bfloat16* __restrict__ residual, const __nv_bfloat16* __restrict__ saved,
                     __nv_bfloat16* __restrict__ y, const __grid_constant__ RowsParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = DELORA_ALIGNED_SMEM(smem_raw);
     uint8_t* smem_a = smem;                                        // 2 halo-tile stages
     uint8_t* smem_w = smem_a + 2 * p.a_stage_bytes;                // filter ring
     float* stage = reinterpret_cast<float*>(smem_w + p.w_stages * kWTileBytes);   // 4 x 4 KB transpose buffers
@@ -88,18 +97,21 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.w_stages;
     const int pitch = p.NS + 2;                                    // pixels per halo-tile row
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;    // CTA (pair) index / count
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1);
-            mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4);
+            mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4 * CG);
         }
         for (int s = 0; s < S; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_ptr_smem, 512);
+    if (warp == 2) { if (CG == 2) tmem_alloc_2sm(tmem_ptr_smem, 512); else tmem_alloc(tmem_ptr_smem, 512); }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync();                                   // peer barriers initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -109,14 +121,20 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             tma_prefetch_desc(&map_x);
             const uint32_t a_bytes = (uint32_t)(pitch * (p.R + 2) * 128);
             uint32_t it = 0;
-            for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x) {
-                const RowsJob j = rows_decode(p, job);
+            for (int job = unit; job < p.n_jobs; job += n_units) {
+                const RowsJob j = rows_decode(p, job, CG);
                 for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
                     const uint32_t s = it & 1;
                     mbar_wait(a_empty + s, ((it >> 1) & 1) ^ 1);
-                    mbar_expect_tx(a_full + s, a_bytes);
-                    // local (row j, pixel c) = padded input pixel (h0 + j, w0 + c)
-                    tma_load_4d(smem_a + s * p.a_stage_bytes, &map_x, a_full + s, kc * 64, j.w0, j.h0, j.b);
+                    // local (row j, pixel c) = padded input pixel (h0 + rank R + j, w0 + c)
+                    if (CG == 2) {
+                        if (rank == 0) mbar_expect_tx(a_full + s, 2 * a_bytes);
+                        tma_load_4d_2sm(smem_a + s * p.a_stage_bytes, &map_x, a_full + s, kc * 64, j.w0,
+                                        j.h0 + (int)rank * p.R, j.b);
+                    } else {
+                        mbar_expect_tx(a_full + s, a_bytes);
+                        tma_load_4d(smem_a + s * p.a_stage_bytes, &map_x, a_full + s, kc * 64, j.w0, j.h0, j.b);
+                    }
                 }
             }
         }
@@ -125,55 +143,80 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (lane == 0) {
             tma_prefetch_desc(&map_w);
             uint32_t it = 0;
-            for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x) {
-                const RowsJob j = rows_decode(p, job);
+            for (int job = unit; job < p.n_jobs; job += n_units) {
+                const RowsJob j = rows_decode(p, job, CG);
                 const RowsPhase& ph = p.phase[j.ph];
+                const int co0 = (j.ct * CG + (int)rank) * 128;
                 for (int kc = 0; kc < p.kchunks; ++kc)
                     for (int t = 0; t < ph.ntaps; ++t, ++it) {
                         const uint32_t s = it % S;
                         mbar_wait(w_empty + s, ((it / S) & 1) ^ 1);
-                        mbar_expect_tx(w_full + s, kWTileBytes);
-                        tma_load_2d(smem_w + s * kWTileBytes, &map_w, w_full + s, (int)ph.wtap[t] * p.Cin + kc * 64,
-                                    j.ct * 128);
+                        if (CG == 2) {
+                            if (rank == 0) mbar_expect_tx(w_full + s, 2 * kWTileBytes);
+                            tma_load_2d_2sm(smem_w + s * kWTileBytes, &map_w, w_full + s, (int)ph.wtap[t] * p.Cin + kc * 64, co0);
+                        } else {
+                            mbar_expect_tx(w_full + s, kWTileBytes);
+                            tma_load_2d(smem_w + s * kWTileBytes, &map_w, w_full + s, (int)ph.wtap[t] * p.Cin + kc * 64, co0);
+                        }
                     }
             }
         }
     } else if (warp == 2) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(128, p.NS, 0, 0);
+        // ===================== MMA issuer (leader CTA of a pair) =====================
+        // The whole warp runs the loop (uniform control flow and operands -> uniform registers, no per-MMA
+        // register -> uniform-register broadcasts); one elected lane issues the tcgen05 instructions.
+        if (rank == 0) {
+            const bool issuer = elect_one();
+            const int N = CG * p.NS;
+            const uint32_t idesc = make_idesc(128 * CG, N, 0, 0);
+            const uint64_t desc_hi = make_smem_desc(0);          // everything but the start-address field
+            const uint32_t row_step = (uint32_t)(pitch * 128) >> 4;             // next tile row, in 16-byte units
             uint32_t a_it = 0, w_it = 0, j_it = 0;
-            for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, ++j_it) {
-                const RowsJob j = rows_decode(p, job);
-                const RowsPhase& ph = p.phase[j.ph];
+            for (int job = unit; job < p.n_jobs; job += n_units, ++j_it) {
+                const int phase_id = job / (p.co_tiles * p.segs_w * p.blocks_h * p.B);
+                const RowsPhase& ph = p.phase[phase_id];
+                const int ntaps = ph.ntaps;
                 const uint32_t ab = j_it & 1;
-                mbar_wait(acc_empty + ab, ((j_it >> 1) & 1) ^ 1);          // epilogue drained this accumulator set
+                mbar_wait(acc_empty + ab, ((j_it >> 1) & 1) ^ 1);          // epilogues drained this accumulator set
                 tc_fence_after();
                 const uint32_t acc = tmem_base + ab * 256;
                 for (int kc = 0; kc < p.kchunks; ++kc, ++a_it) {
                     const uint32_t as = a_it & 1;
                     mbar_wait(a_full + as, (a_it >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(smem_a + as * p.a_stage_bytes);
-                    for (int t = 0; t < ph.ntaps; ++t, ++w_it) {
+                    const uint32_t a_lo = (smem_u32(smem_a + as * p.a_stage_bytes) & 0x3FFFFu) >> 4;
+                    for (int t = 0; t < ntaps; ++t, ++w_it) {
                         const uint32_t ws = w_it % S;
                         mbar_wait(w_full + ws, (w_it / S) & 1);
                         tc_fence_after();
-                        const uint64_t dw = make_smem_desc(smem_u32(smem_w + ws * kWTileBytes));
-                        const uint32_t tap_off = (uint32_t)(((int)ph.drow[t] * pitch + (int)ph.dcol[t]) * 128);
+                        const uint32_t w_lo = (smem_u32(smem_w + ws * kWTileBytes) & 0x3FFFFu) >> 4;
+                        const uint32_t x_lo = a_lo + (uint32_t)(((int)ph.drow[t] * pitch + (int)ph.dcol[t]) * 8);
                         const uint32_t first = (kc == 0 && t == 0) ? 0u : 1u;
-                        for (int i = 0; i < p.R; ++i) {
-                            const uint64_t dx = make_smem_desc(a_base + tap_off + (uint32_t)(i * pitch * 128));
+                        if (issuer) {
+                            for (int i = 0; i < p.R; ++i) {
+                                const uint64_t dw = desc_hi | (uint64_t)w_lo;
+                                const uint64_t dx = desc_hi | (uint64_t)(x_lo + (uint32_t)i * row_step);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)          // 64 channels = 4 x K16; +32 bytes = +2 in 16-byte units
-                                tcgen05_mma_bf16(acc + (uint32_t)(i * p.NS), dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2),
-                                                 idesc, (k > 0) ? 1u : first);
+                                for (int k = 0; k < 4; ++k) {    // 64 channels = 4 x K16; +32 bytes = +2 in 16-byte units
+                                    if (CG == 2)
+                                        tcgen05_mma_bf16_2sm(acc + (uint32_t)(i * N), dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2),
+                                                             idesc, (k > 0) ? 1u : first);
+                                    else
+                                        tcgen05_mma_bf16(acc + (uint32_t)(i * N), dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2),
+                                                         idesc, (k > 0) ? 1u : first);
+                                }
+                            }
+                            if (CG == 2) tcgen05_commit_2sm(w_empty + ws); else tcgen05_commit(w_empty + ws);
+                            if (t == ntaps - 1) {                // halo tile free after this chunk's last tap
+                                if (CG == 2) tcgen05_commit_2sm(a_empty + as); else tcgen05_commit(a_empty + as);
+                                if (kc == p.kchunks - 1) {       // accumulators of this job complete
+                                    if (CG == 2) tcgen05_commit_2sm(acc_full + ab); else tcgen05_commit(acc_full + ab);
+                                }
+                            }
                         }
-                        tcgen05_commit(w_empty + ws);            // filter stage free when these MMAs retire
+                        __syncwarp();
                     }
-                    tcgen05_commit(a_empty + as);                // halo tile free
                 }
-                tcgen05_commit(acc_full + ab);                   // accumulators of this job complete
             }
         }
     } else {
@@ -181,16 +224,27 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const int quarter = warp & 3;                            // TMEM lanes 32*quarter .. +31 = output channels
         float* st = stage + quarter * 1024;
         const int Wp = p.Wout + 2, Hp = p.Hout + 2;
-        const int n_blocks = (p.R * p.NS) >> 5;
+        const int n_blocks = (CG * p.R * p.NS) >> 5;
         uint32_t j_it = 0;
-        for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, ++j_it) {
-            const RowsJob j = rows_decode(p, job);
+        for (int job = unit; job < p.n_jobs; job += n_units, ++j_it) {
+            const RowsJob j = rows_decode(p, job, CG);
             const RowsPhase& ph = p.phase[j.ph];
             const uint32_t ab = j_it & 1;
             mbar_wait(acc_full + ab, (j_it >> 1) & 1);
             tc_fence_after();
-            const int c_first = j.ct * 128 + quarter * 32;
+            const int c_first = (j.ct * CG + (int)rank) * 128 + quarter * 32;
             for (int cb = 0; cb < n_blocks; ++cb) {
+                // this thread's pixel of the block; its residual / saved loads go out before the TMEM read
+                // accumulator column -> (row i of the job, CTA half, pixel): columns of MMA i are [i][half][NS]
+                const int col = cb * 32 + lane;
+                const int blk = col / p.NS, wl = col - blk * p.NS;
+                const int i = blk / CG, half = blk - i * CG;
+                const int hg = j.h0 + half * p.R + i, wg = j.w0 + wl;
+                const int ho = hg * p.out_sh + ph.oh, wo = wg * p.out_sw + ph.ow;
+                const bool in_range = hg < p.Hg && wg < p.Wg && ho < p.Hout && wo < p.Wout;
+                const size_t off = (((size_t)j.b * Hp + (ho + 1)) * Wp + (wo + 1)) * p.Cout + c_first;
+                EpiloguePrefetch pf;
+                if (in_range) epilogue_prefetch32(pf, residual, saved, off, p.act);
                 uint32_t acc[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * 256 + (uint32_t)(cb * 32), acc);
                 // transpose: thread = channel `lane` holds 32 pixels -> thread = pixel `lane` holds 32 channels.
@@ -202,23 +256,19 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
                 for (int c = 0; c < 32; ++c) v[c] = st[lane * 32 + (c ^ lane)];
                 __syncwarp();
-                const int col = cb * 32 + lane;
-                const int i = col / p.NS, wl = col - i * p.NS;
-                const int hg = j.h0 + i, wg = j.w0 + wl;
-                const int ho = hg * p.out_sh + ph.oh, wo = wg * p.out_sw + ph.ow;
-                if (hg < p.Hg && wg < p.Wg && ho < p.Hout && wo < p.Wout) {
-                    const size_t pix = ((size_t)j.b * Hp + (ho + 1)) * Wp + (wo + 1);
-                    epilogue_store32(v, residual, saved, y, pix * p.Cout + c_first, p.act, wo == 0, wo == p.Wout - 1,
-                                     (size_t)p.Wout * p.Cout);
-                }
+                if (in_range)
+                    epilogue_finish32(v, pf, residual != nullptr, y, off, p.act, wo == 0, wo == p.Wout - 1,
+                                      (size_t)p.Wout * p.Cout);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + ab);
+            if (lane == 0) { if (CG == 2) mbar_arrive_leader(acc_empty + ab); else mbar_arrive(acc_empty + ab); }
         }
     }
+    tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (CG == 2) cluster_sync();                                 // the peer may still be reading / signalling
+    if (warp == 2) { if (CG == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // ---------------------------------------------------------------- host side
@@ -277,17 +327,31 @@ static const RowsMapEntry* rows_get_maps(const RowsMapKey& key) {
 
 // segment width / rows per job for a job grid of Hg x Wg positions: NS = multiple of 16 covering the row in equal
 // segments of at most 128 pixels; R rows so that R * NS <= 256 accumulator columns (a multiple of 32)
-static void rows_pick_tile(int Hg, int Wg, int* NS, int* R) {
+static void rows_pick_tile(int Hg, int Wg, int cg, int* NS, int* R) {
     const int segs = (Wg + 127) / 128;
     int ns = ((Wg + segs - 1) / segs + 15) / 16 * 16;
     if (ns < 16) ns = 16;
-    int r = 256 / ns;
+    int r = 256 / (ns * cg);
+    if (r < 1) r = 1;
+    if (cg == 2) {                                  // columns per job = 2 R NS (a multiple of 32 for NS % 16 == 0)
+        while (r > 1 && 2 * (r - 1) >= Hg) --r;     // no more rows than the image has
+        *NS = ns; *R = r;
+        return;
+    }
     if ((r * ns) % 32 != 0) r -= 1;
     if (r > Hg) r = Hg;
     if (r < 1) r = 1;
     while ((r * ns) % 32 != 0) ++r;                 // r = 1 with ns % 32 == 16: take two rows (second one masked)
     *NS = ns; *R = r;
 }
+
+// DELORA_CONV_PAIRS=0 (or delora_conv_select_kernel(2)) keeps the single-CTA form for every layer
+static int g_rows_pairs = -1;
+bool rows_use_pairs() {
+    if (g_rows_pairs < 0) { const char* e = getenv("DELORA_CONV_PAIRS"); g_rows_pairs = (e && e[0] == '0') ? 0 : 1; }
+    return g_rows_pairs == 1;
+}
+void rows_set_pairs(int on) { g_rows_pairs = on ? 1 : 0; }
 
 bool conv_rows_eligible(int Cin, int Cout, int ksize) {
     return Cin % 64 == 0 && Cout % 128 == 0 && (ksize == 3 || ksize == 1);
@@ -337,10 +401,11 @@ int conv_rows_launch(const void* x, const void* w, const void* residual, const v
                 }
         p.n_phases = np;
     }
-    rows_pick_tile(p.Hg, p.Wg, &p.NS, &p.R);
+    const int cg = (Cout % 256 == 0 && rows_use_pairs()) ? 2 : 1;
+    rows_pick_tile(p.Hg, p.Wg, cg, &p.NS, &p.R);
     p.segs_w = (p.Wg + p.NS - 1) / p.NS;
-    p.blocks_h = (p.Hg + p.R - 1) / p.R;
-    p.co_tiles = Cout / 128;
+    p.blocks_h = (p.Hg + p.R * cg - 1) / (p.R * cg);
+    p.co_tiles = Cout / (128 * cg);
     p.kchunks = Cin / 64;
     p.n_jobs = p.n_phases * B * p.blocks_h * p.segs_w * p.co_tiles;
     p.a_stage_bytes = (((p.NS + 2) * (p.R + 2) * 128) + 1023) / 1024 * 1024;
@@ -357,13 +422,26 @@ int conv_rows_launch(const void* x, const void* w, const void* residual, const v
     cudaGetDevice(&dev);
     static bool attr_set[64] = {};
     if (dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_rows_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_rows_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         DELORA_CHECK_ARG(e == cudaSuccess, "conv_rows: shared-memory opt-in failed: %s", cudaGetErrorString(e));
         attr_set[dev] = true;
     }
-    const int grid = p.n_jobs < kNumSMs ? p.n_jobs : kNumSMs;
-    conv_rows_tc_kernel<<<grid, kRowsThreads, smem, stream>>>(maps->mx, maps->mw, (const __nv_bfloat16*)residual,
-                                                               (const __nv_bfloat16*)saved, (__nv_bfloat16*)y, p);
+    const int units = kNumSMs / cg;
+    const int grid = (p.n_jobs < units ? p.n_jobs : units) * cg;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kRowsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const __nv_bfloat16* res_p = (const __nv_bfloat16*)residual;
+    const __nv_bfloat16* sav_p = (const __nv_bfloat16*)saved;
+    __nv_bfloat16* y_p = (__nv_bfloat16*)y;
+    cudaError_t le = (cg == 2) ? cudaLaunchKernelEx(&cfg, conv_rows_tc_kernel<2>, maps->mx, maps->mw, res_p, sav_p, y_p, p)
+                               : cudaLaunchKernelEx(&cfg, conv_rows_tc_kernel<1>, maps->mx, maps->mw, res_p, sav_p, y_p, p);
+    DELORA_CHECK_ARG(le == cudaSuccess, "conv_rows: launch failed: %s", cudaGetErrorString(le));
     DELORA_CHECK_LAUNCH("conv_rows_tc_kernel");
     return 0;
 }

@@ -718,6 +718,7 @@ static const TensorMaps* get_maps(const void* x, const void* w, int B, int Hin, 
 
 namespace delora {
 bool conv_rows_eligible(int Cin, int Cout, int ksize);
+void rows_set_pairs(int on);
 int conv_rows_launch(const void* x, const void* w, const void* residual, const void* saved, void* y, int B, int Hout,
                      int Wout, int Cin, int Cout, int ksize, int up_h, int up_w, int act, cudaStream_t stream);
 // DELORA_CONV_ROWS=0 keeps every convolution on the first-generation kernel (A/B measurements)
@@ -732,7 +733,8 @@ using namespace delora;
 
 extern "C" int delora_conv_select_kernel(int rows_kernel) {
     const int prev = use_conv_rows() ? 1 : 0;
-    if (rows_kernel == 0 || rows_kernel == 1) g_conv_rows = rows_kernel;
+    if (rows_kernel == 0 || rows_kernel == 1) { g_conv_rows = rows_kernel; rows_set_pairs(1); }
+    if (rows_kernel == 2) { g_conv_rows = 1; rows_set_pairs(0); }          // row-block kernel, single CTAs only
     return prev;
 }
 

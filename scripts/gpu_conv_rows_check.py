@@ -54,10 +54,13 @@ def check_fprop(b, cin, cout, h, w, k, act, use_res, time_it=True):
         out = ops.padded_nhwc_zeros(b, h, w, cout, DEV)
         L.delora_conv_select_kernel(0)
         t_old = timed(lambda: ops.conv2d_fprop(x, wt, h, w, k, (1, 1), act, res, out, saved))
+        L.delora_conv_select_kernel(2)
+        t_one = timed(lambda: ops.conv2d_fprop(x, wt, h, w, k, (1, 1), act, res, out, saved))
         L.delora_conv_select_kernel(1)
         t_new = timed(lambda: ops.conv2d_fprop(x, wt, h, w, k, (1, 1), act, res, out, saved))
         fl = 2.0 * b * h * w * cout * cin * k * k
-        msg += f" | old {t_old * 1e3:.1f} us ({fl / t_old / 1e9:.0f} TF/s)  new {t_new * 1e3:.1f} us ({fl / t_new / 1e9:.0f} TF/s)"
+        msg += (f" | old {t_old * 1e3:.1f} us ({fl / t_old / 1e9:.0f} TF/s)  rows-1cta {t_one * 1e3:.1f} us "
+                f"({fl / t_one / 1e9:.0f})  rows-pairs {t_new * 1e3:.1f} us ({fl / t_new / 1e9:.0f} TF/s)")
     print(("OK   " if bad == 0 else "FAIL ") + msg, flush=True)
     return bad == 0
 
@@ -76,7 +79,9 @@ def check_dgrad(b, cin, cout, h, w, stride, act, use_res, time_it=True):
         src = dz if stride == (1, 1) else ops.zero_upsample(dz, ho, wo, stride, None, (h, w))
         return ops.conv2d_fprop(src, wf, h, w, 3, (1, 1), act, res, out, saved)
     y_old = old()
+    L.delora_conv_select_kernel(1)
     y_new = ops.conv2d_dgrad(dz, wf, h, w, stride, act, res, None, saved)
+    L.delora_conv_select_kernel(0)
     torch.cuda.synchronize()
     d = (y_new.float() - y_old.float()).abs()
     ref = y_old.float().abs().max().item()
@@ -85,9 +90,13 @@ def check_dgrad(b, cin, cout, h, w, stride, act, use_res, time_it=True):
     if time_it:
         out = ops.padded_nhwc_zeros(b, h, w, cin, DEV)
         t_old = timed(lambda: old(out))
+        L.delora_conv_select_kernel(2)
+        t_one = timed(lambda: ops.conv2d_dgrad(dz, wf, h, w, stride, act, res, out, saved))
+        L.delora_conv_select_kernel(1)
         t_new = timed(lambda: ops.conv2d_dgrad(dz, wf, h, w, stride, act, res, out, saved))
         fl = 2.0 * b * ho * wo * cout * cin * 9
-        msg += f" | old {t_old * 1e3:.1f} us  new {t_new * 1e3:.1f} us ({fl / t_new / 1e9:.0f} TF/s useful)"
+        msg += (f" | old {t_old * 1e3:.1f} us  rows-1cta {t_one * 1e3:.1f} us  rows-pairs {t_new * 1e3:.1f} us "
+                f"({fl / t_new / 1e9:.0f} TF/s useful)")
     L.delora_conv_select_kernel(1)
     print(("OK   " if bad == 0 else "FAIL ") + msg, flush=True)
     return bad == 0
@@ -109,6 +118,9 @@ def main():
     ok &= check_dgrad(1, 256, 512, 16, 64, (2, 2), 3, True, False)
     ok &= check_dgrad(1, 256, 512, 15, 46, (2, 2), 0, False, False)
     ok &= check_dgrad(1, 128, 128, 8, 96, (1, 1), 4, True, False)
+    ok &= check_fprop(1, 64, 256, 3, 40, 3, 2, True, False)
+    ok &= check_fprop(3, 128, 512, 9, 23, 3, 1, True, False)
+    ok &= check_dgrad(2, 256, 128, 10, 180, (1, 2), 3, True, False)
     print(f"-- small cases done in {time.time() - t0:.1f} s, ok={ok}", flush=True)
     if not quick:
         # bench shapes (B = 16, 64x2048 image): L2 128ch @64x256, L3 256ch @64x128, L4 512ch @32x64
