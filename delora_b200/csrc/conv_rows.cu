@@ -53,6 +53,8 @@ struct RowsParams {
     int act;
     int w_stages;
     int a_stage_bytes;
+    int res_grid;                                  // 1: `residual` is given on the job grid [B, Hg+2, Wg+2, Cout] and belongs
+                                                   //    to phase (0, 0) only (data gradient of a 1x1 strided downsample)
     RowsPhase phase[kRowsMaxPhases];
 };
 
@@ -167,56 +169,68 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         // register -> uniform-register broadcasts); one elected lane issues the tcgen05 instructions.
         if (rank == 0) {
             const bool issuer = elect_one();
-            const int N = CG * p.NS;
+            const int N = CG * p.NS, R = p.R, kchunks = p.kchunks;
             const uint32_t idesc = make_idesc(128 * CG, N, 0, 0);
             const uint64_t desc_hi = make_smem_desc(0);          // everything but the start-address field
             const uint32_t row_step = (uint32_t)(pitch * 128) >> 4;             // next tile row, in 16-byte units
-            uint32_t a_it = 0, w_it = 0, j_it = 0;
-            for (int job = unit; job < p.n_jobs; job += n_units, ++j_it) {
-                const int phase_id = job / (p.co_tiles * p.segs_w * p.blocks_h * p.B);
-                const RowsPhase& ph = p.phase[phase_id];
-                const int ntaps = ph.ntaps;
-                const uint32_t ab = j_it & 1;
-                mbar_wait(acc_empty + ab, ((j_it >> 1) & 1) ^ 1);          // epilogues drained this accumulator set
+            const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4, a_step = (uint32_t)p.a_stage_bytes >> 4;
+            const uint32_t w_lo0 = (smem_u32(smem_w) & 0x3FFFFu) >> 4;
+            const int jobs_per_phase = p.co_tiles * p.segs_w * p.blocks_h * p.B;
+            uint32_t as = 0, aph = 0, ws = 0, wph = 0, ab = 0, accph = 0;      // ring slots and phase bits
+            int cur_phase = -1, ntaps = 0;
+            uint32_t xoff[kRowsMaxTaps];                         // tap offsets inside the halo tile, 16-byte units
+            for (int job = unit; job < p.n_jobs; job += n_units) {
+                const int phase_id = job / jobs_per_phase;
+                if (phase_id != cur_phase) {
+                    cur_phase = phase_id;
+                    const RowsPhase& ph = p.phase[phase_id];
+                    ntaps = ph.ntaps;
+#pragma unroll
+                    for (int t = 0; t < kRowsMaxTaps; ++t) xoff[t] = (uint32_t)(((int)ph.drow[t] * pitch + (int)ph.dcol[t]) * 8);
+                }
+                mbar_wait(acc_empty + ab, accph ^ 1);            // epilogues drained this accumulator set
                 tc_fence_after();
                 const uint32_t acc = tmem_base + ab * 256;
-                for (int kc = 0; kc < p.kchunks; ++kc, ++a_it) {
-                    const uint32_t as = a_it & 1;
-                    mbar_wait(a_full + as, (a_it >> 1) & 1);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(a_full + as, aph);
                     tc_fence_after();
-                    const uint32_t a_lo = (smem_u32(smem_a + as * p.a_stage_bytes) & 0x3FFFFu) >> 4;
-                    for (int t = 0; t < ntaps; ++t, ++w_it) {
-                        const uint32_t ws = w_it % S;
-                        mbar_wait(w_full + ws, (w_it / S) & 1);
-                        tc_fence_after();
-                        const uint32_t w_lo = (smem_u32(smem_w + ws * kWTileBytes) & 0x3FFFFu) >> 4;
-                        const uint32_t x_lo = a_lo + (uint32_t)(((int)ph.drow[t] * pitch + (int)ph.dcol[t]) * 8);
-                        const uint32_t first = (kc == 0 && t == 0) ? 0u : 1u;
-                        if (issuer) {
-                            for (int i = 0; i < p.R; ++i) {
-                                const uint64_t dw = desc_hi | (uint64_t)w_lo;
-                                const uint64_t dx = desc_hi | (uint64_t)(x_lo + (uint32_t)i * row_step);
+                    const uint32_t a_lo = a_lo0 + as * a_step;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {    // 64 channels = 4 x K16; +32 bytes = +2 in 16-byte units
-                                    if (CG == 2)
-                                        tcgen05_mma_bf16_2sm(acc + (uint32_t)(i * N), dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2),
+                    for (int t = 0; t < kRowsMaxTaps; ++t) {
+                        if (t < ntaps) {
+                            mbar_wait(w_full + ws, wph);
+                            tc_fence_after();
+                            if (issuer) {
+                                const uint64_t dw = desc_hi | (uint64_t)(w_lo0 + ws * (kWTileBytes >> 4));
+                                const uint32_t x_lo = a_lo + xoff[t];
+                                const uint32_t first = (kc == 0 && t == 0) ? 0u : 1u;
+                                for (int i = 0; i < R; ++i) {
+                                    const uint64_t dx = desc_hi | (uint64_t)(x_lo + (uint32_t)i * row_step);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {   // 64 channels = 4 x K16; +32 bytes = +2 in 16-byte units
+                                        if (CG == 2)
+                                            tcgen05_mma_bf16_2sm(acc + (uint32_t)(i * N), dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2),
+                                                                 idesc, (k > 0) ? 1u : first);
+                                        else
+                                            tcgen05_mma_bf16(acc + (uint32_t)(i * N), dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2),
                                                              idesc, (k > 0) ? 1u : first);
-                                    else
-                                        tcgen05_mma_bf16(acc + (uint32_t)(i * N), dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2),
-                                                         idesc, (k > 0) ? 1u : first);
+                                    }
+                                }
+                                if (CG == 2) tcgen05_commit_2sm(w_empty + ws); else tcgen05_commit(w_empty + ws);
+                                if (t == ntaps - 1) {            // halo tile free after this chunk's last tap
+                                    if (CG == 2) tcgen05_commit_2sm(a_empty + as); else tcgen05_commit(a_empty + as);
+                                    if (kc == kchunks - 1) {     // accumulators of this job complete
+                                        if (CG == 2) tcgen05_commit_2sm(acc_full + ab); else tcgen05_commit(acc_full + ab);
+                                    }
                                 }
                             }
-                            if (CG == 2) tcgen05_commit_2sm(w_empty + ws); else tcgen05_commit(w_empty + ws);
-                            if (t == ntaps - 1) {                // halo tile free after this chunk's last tap
-                                if (CG == 2) tcgen05_commit_2sm(a_empty + as); else tcgen05_commit(a_empty + as);
-                                if (kc == p.kchunks - 1) {       // accumulators of this job complete
-                                    if (CG == 2) tcgen05_commit_2sm(acc_full + ab); else tcgen05_commit(acc_full + ab);
-                                }
-                            }
+                            __syncwarp();
+                            if (++ws == (uint32_t)S) { ws = 0; wph ^= 1; }
                         }
-                        __syncwarp();
                     }
+                    as ^= 1; aph ^= (as == 0);
                 }
+                ab ^= 1; accph ^= (ab == 0);
             }
         }
     } else {
@@ -243,8 +257,11 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 const int ho = hg * p.out_sh + ph.oh, wo = wg * p.out_sw + ph.ow;
                 const bool in_range = hg < p.Hg && wg < p.Wg && ho < p.Hout && wo < p.Wout;
                 const size_t off = (((size_t)j.b * Hp + (ho + 1)) * Wp + (wo + 1)) * p.Cout + c_first;
+                const bool use_res = residual != nullptr && (!p.res_grid || (ph.oh | ph.ow) == 0);
+                const size_t roff = p.res_grid
+                    ? (((size_t)j.b * (p.Hg + 2) + (hg + 1)) * (p.Wg + 2) + (wg + 1)) * p.Cout + c_first : off;
                 EpiloguePrefetch pf;
-                if (in_range) epilogue_prefetch32(pf, residual, saved, off, p.act);
+                if (in_range) epilogue_prefetch32(pf, use_res ? residual + roff : nullptr, saved + (p.act >= 3 ? off : 0), 0, p.act);
                 uint32_t acc[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * 256 + (uint32_t)(cb * 32), acc);
                 // transpose: thread = channel `lane` holds 32 pixels -> thread = pixel `lane` holds 32 channels.
@@ -257,7 +274,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 for (int c = 0; c < 32; ++c) v[c] = st[lane * 32 + (c ^ lane)];
                 __syncwarp();
                 if (in_range)
-                    epilogue_finish32(v, pf, residual != nullptr, y, off, p.act, wo == 0, wo == p.Wout - 1,
+                    epilogue_finish32(v, pf, use_res, y, off, p.act, wo == 0, wo == p.Wout - 1,
                                       (size_t)p.Wout * p.Cout);
             }
             tc_fence_before();
@@ -360,9 +377,11 @@ bool conv_rows_eligible(int Cin, int Cout, int ksize) {
 // stride-1 convolution (up_h = up_w = 1) or data gradient of a stride-(up_h, up_w) 3x3 convolution (x = output
 // gradient of that convolution, w = its flipped / transposed filter [Cout][9][Cin], y = input gradient Hout x Wout)
 int conv_rows_launch(const void* x, const void* w, const void* residual, const void* saved, void* y, int B, int Hout,
-                     int Wout, int Cin, int Cout, int ksize, int up_h, int up_w, int act, cudaStream_t stream) {
+                     int Wout, int Cin, int Cout, int ksize, int up_h, int up_w, int act, cudaStream_t stream,
+                     int residual_on_grid) {
     RowsParams p;
     memset(&p, 0, sizeof(p));
+    p.res_grid = (residual_on_grid && (up_h > 1 || up_w > 1)) ? 1 : 0;
     p.B = B; p.Cin = Cin; p.Cout = Cout; p.Hout = Hout; p.Wout = Wout; p.act = act;
     p.out_sh = up_h; p.out_sw = up_w;
     p.Hg = (Hout + up_h - 1) / up_h; p.Wg = (Wout + up_w - 1) / up_w;
@@ -452,7 +471,7 @@ using namespace delora;
 
 extern "C" int delora_conv2d_dgrad_bf16(const void* dz, const void* w_flip, const void* residual, const void* saved,
                                         void* dx, int B, int Hin, int Win, int Cin, int Cout, int stride_h, int stride_w,
-                                        int act, void* stream) {
+                                        int act, int residual_strided, void* stream) {
     // Cin / Cout are those of the FORWARD convolution: dz has Cout channels, dx has Cin channels
     DELORA_CHECK_ARG(dz && w_flip && dx, "delora_conv2d_dgrad_bf16: null pointer");
     DELORA_CHECK_ARG(act >= 0 && act <= 4 && (act < 3 || saved), "delora_conv2d_dgrad_bf16: act=%d (3/4 need `saved`)", act);
@@ -462,5 +481,5 @@ extern "C" int delora_conv2d_dgrad_bf16(const void* dz, const void* w_flip, cons
     DELORA_CHECK_ARG(conv_rows_eligible(Cout, Cin, 3),
                      "delora_conv2d_dgrad_bf16: needs Cin %% 128 == 0 and Cout %% 64 == 0 (got Cin=%d, Cout=%d)", Cin, Cout);
     return conv_rows_launch(dz, w_flip, residual, saved, dx, B, Hin, Win, Cout, Cin, 3, stride_h, stride_w, act,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, residual_strided);
 }

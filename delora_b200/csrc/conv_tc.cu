@@ -720,7 +720,8 @@ namespace delora {
 bool conv_rows_eligible(int Cin, int Cout, int ksize);
 void rows_set_pairs(int on);
 int conv_rows_launch(const void* x, const void* w, const void* residual, const void* saved, void* y, int B, int Hout,
-                     int Wout, int Cin, int Cout, int ksize, int up_h, int up_w, int act, cudaStream_t stream);
+                     int Wout, int Cin, int Cout, int ksize, int up_h, int up_w, int act, cudaStream_t stream,
+                     int residual_on_grid);
 // DELORA_CONV_ROWS=0 keeps every convolution on the first-generation kernel (A/B measurements)
 static int g_conv_rows = -1;
 static bool use_conv_rows() {
@@ -749,7 +750,7 @@ extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void
     DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin >= 1 && Win >= 1,
                      "delora_conv2d_fprop_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
     if (stride_h == 1 && stride_w == 1 && conv_rows_eligible(Cin, Cout, ksize) && use_conv_rows())
-        return conv_rows_launch(x, w, residual, saved, y, B, Hin, Win, Cin, Cout, ksize, 1, 1, act, (cudaStream_t)stream);
+        return conv_rows_launch(x, w, residual, saved, y, B, Hin, Win, Cin, Cout, ksize, 1, 1, act, (cudaStream_t)stream, 0);
     ConvParams p;
     p.B = B; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
     p.stride_h = stride_h; p.stride_w = stride_w; p.pad_off = (ksize == 1) ? 1 : 0; p.act = act;

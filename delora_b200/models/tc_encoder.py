@@ -239,6 +239,14 @@ class TensorCoreEncoder:
                 # strided positions afterwards (2-4x fewer MMAs than convolving the zero-upsampled gradient)
                 small = ops.conv2d_fprop(dz2, blk["fd"], oh, ow, 1, (1, 1), ops.ACT_NONE, None,
                                          self._buffer(f"g{i}ds", b, oh, ow, cin, dev))
+                if i > 0 and ops.conv2d_dgrad_eligible(cin, cout, cw, (sh, sw)):
+                    # phase-decomposed data gradient of the strided conv1: no zero-upsampled tensors, the downsample's
+                    # gradient enters as a residual on the (sh*h, sw*w) pixels, act' of the block input in the epilogue
+                    dz2 = ops.conv2d_dgrad(dz1, blk["f1"], ch, cw, (sh, sw), act_bwd, small,
+                                           self._buffer(f"g{i}x", b, ch, cw, cin, dev), saved=blk["x"],
+                                           residual_strided=True)
+                    grads_rev.append((g_w1, g_w2, g_wd))
+                    continue
                 resid = ops.zero_upsample(small, oh, ow, (sh, sw), self._buffer(f"g{i}d", b, ch, cw, cin, dev), (ch, cw))
                 src = ops.zero_upsample(dz1, oh, ow, (sh, sw), self._buffer(f"g{i}u1", b, ch, cw, cout, dev), (ch, cw))
             else:

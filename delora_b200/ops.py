@@ -301,8 +301,10 @@ def conv2d_dgrad_eligible(cin, cout, win, stride):
     return cin % 128 == 0 and cout % 64 == 0 and (stride[1] == 1 or win % 2 == 0)
 
 
-def conv2d_dgrad(dz, w_flip, hin, win, stride, act=ACT_NONE, residual=None, out=None, saved=None):
-    """dz [B,Hout+2,Wout+2,Cout], w_flip [Cin,9,Cout] -> dx [B,Hin+2,Win+2,Cin] (3x3 conv of `stride`)."""
+def conv2d_dgrad(dz, w_flip, hin, win, stride, act=ACT_NONE, residual=None, out=None, saved=None,
+                 residual_strided=False):
+    """dz [B,Hout+2,Wout+2,Cout], w_flip [Cin,9,Cout] -> dx [B,Hin+2,Win+2,Cin] (3x3 conv of `stride`).
+    residual_strided: `residual` has dz's spatial size and lands on the pixels (sh*h, sw*w) only."""
     b, _, _, cout = dz.shape
     cin = w_flip.shape[0]
     if out is None:
@@ -312,7 +314,7 @@ def conv2d_dgrad(dz, w_flip, hin, win, stride, act=ACT_NONE, residual=None, out=
                                           _req(residual, torch.bfloat16, "residual") if residual is not None else None,
                                           _req(saved, torch.bfloat16, "saved") if saved is not None else None,
                                           out.data_ptr(), b, hin, win, cin, cout, stride[0], stride[1], int(act),
-                                          _stream()), "delora_conv2d_dgrad_bf16")
+                                          1 if residual_strided else 0, _stream()), "delora_conv2d_dgrad_bf16")
     return out
 
 

@@ -253,11 +253,14 @@ int delora_conv_select_kernel(int rows_kernel);
  * subset of flipped taps that hits non-zero positions; no zero-upsampled tensor is materialised.
  * dz [B,Hout+2,Wout+2,Cout] (Hout = (Hin-1)/stride_h + 1 ...), w_flip [Cin, 9, Cout] (delora_conv_weight_prep_bf16),
  * residual / saved / dx [B,Hin+2,Win+2,Cin]; act as in delora_conv2d_fprop_bf16 (3 / 4 = multiply by act'(saved)).
+ * residual_strided = 1: `residual` is [B,Hout+2,Wout+2,Cin] instead and is added at the input pixels
+ * (stride_h * h, stride_w * w) only -- the data gradient of the block's 1x1 strided downsample (:134), which never
+ * reaches the other pixels (replaces a zero-upsampled copy of it).
  * Needs Cin % 128 == 0, Cout % 64 == 0 and, for stride_w = 2, an even Win (an odd circular width mixes the phases at
  * the seam: use delora_zero_upsample_nhwc_bf16 + delora_conv2d_fprop_bf16 there). */
 int delora_conv2d_dgrad_bf16(const void* dz, const void* w_flip, const void* residual, const void* saved, void* dx,
                              int B, int Hin, int Win, int Cin, int Cout, int stride_h, int stride_w, int act,
-                             void* stream);
+                             int residual_strided, void* stream);
 /* Weight gradient of the same convolution on tcgen05 (split-K over pixels, deterministic reduction):
  * x [B,Hin+2,Win+2,Cin] padded NHWC bf16 (the layer input), dz [B,Hout+2,Wout+2,Cout] padded NHWC bf16
  * (gradient w.r.t. the pre-activation output) -> dw [Cout, Cin_true, k, k] fp32 (torch layout; Cin_true <= Cin
