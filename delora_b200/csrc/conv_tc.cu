@@ -719,6 +719,10 @@ static const TensorMaps* get_maps(const void* x, const void* w, int B, int Hin, 
 namespace delora {
 bool conv_rows_eligible(int Cin, int Cout, int ksize);
 void rows_set_pairs(int on);
+bool wgrad2_eligible(int Cin, int Cout, int ksize, int stride_h, int stride_w);
+int64_t wgrad2_scratch_floats(int B, int Hout, int Wout, int Cin, int Cout, int sw);
+int wgrad2_launch(const void* x, const void* dz, float* dw, float* scratch, int B, int Hin, int Win, int Cin, int Cin_true,
+                  int Cout, int stride_h, int stride_w, cudaStream_t st);
 int conv_rows_launch(const void* x, const void* w, const void* residual, const void* saved, void* y, int B, int Hout,
                      int Wout, int Cin, int Cout, int ksize, int up_h, int up_w, int act, cudaStream_t stream,
                      int residual_on_grid);
@@ -828,7 +832,13 @@ static int wgrad_splits(int B, int Hout, int Wout, int Cin, int Cout, int ksize)
 }
 
 extern "C" int64_t delora_conv2d_wgrad_scratch_floats(int B, int Hout, int Wout, int Cin, int Cout, int ksize) {
-    return (int64_t)wgrad_splits(B, Hout, Wout, Cin, Cout, ksize) * ksize * ksize * Cout * Cin;
+    int64_t n = (int64_t)wgrad_splits(B, Hout, Wout, Cin, Cout, ksize) * ksize * ksize * Cout * Cin;
+    if (wgrad2_eligible(Cin, Cout, ksize, 1, 1)) {           // either kernel may run (delora_conv_select_kernel)
+        const int64_t n1 = wgrad2_scratch_floats(B, Hout, Wout, Cin, Cout, 1), n2 = wgrad2_scratch_floats(B, Hout, Wout, Cin, Cout, 2);
+        n = n > n1 ? n : n1;
+        n = n > n2 ? n : n2;
+    }
+    return n;
 }
 
 extern "C" int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw, float* scratch, int B, int Hin, int Win,
@@ -840,6 +850,8 @@ extern "C" int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw
                      "delora_conv2d_wgrad_bf16: Cin=%d, Cout=%d must be multiples of 64", Cin, Cout);
     DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin >= 1 && Win >= 1,
                      "delora_conv2d_wgrad_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
+    if (use_conv_rows() && wgrad2_eligible(Cin, Cout, ksize, stride_h, stride_w))
+        return wgrad2_launch(x, dz, dw, scratch, B, Hin, Win, Cin, Cin_true, Cout, stride_h, stride_w, (cudaStream_t)stream);
     WgradParams p;
     p.B = B; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
     p.stride_h = stride_h; p.stride_w = stride_w; p.pad_off = (ksize == 1) ? 1 : 0;

@@ -102,6 +102,32 @@ def check_dgrad(b, cin, cout, h, w, stride, act, use_res, time_it=True):
     return bad == 0
 
 
+def check_wgrad(b, cin, cout, h, w, stride, time_it=True):
+    gen = torch.Generator(device=DEV).manual_seed(cin + cout + h + w + 2)
+    ho, wo = ops.conv_out_size(h, stride[0]), ops.conv_out_size(w, stride[1])
+    x = rand_padded(b, h, w, cin, gen)
+    dz = rand_padded(b, ho, wo, cout, gen)
+    L.delora_conv_select_kernel(0)
+    g_old = ops.conv2d_wgrad(x, dz, h, w, 3, stride).clone()
+    L.delora_conv_select_kernel(1)
+    g_new = ops.conv2d_wgrad(x, dz, h, w, 3, stride).clone()
+    torch.cuda.synchronize()
+    d = (g_new - g_old).abs().max().item()
+    ref = g_old.abs().max().item()
+    ok = d <= 1e-3 * ref
+    msg = f"wgrad B{b} {cin}->{cout} in {h}x{w} s{stride}: maxdiff {d:.4g} (ref max {ref:.4g})"
+    if time_it:
+        L.delora_conv_select_kernel(0)
+        t_old = timed(lambda: ops.conv2d_wgrad(x, dz, h, w, 3, stride))
+        L.delora_conv_select_kernel(1)
+        t_new = timed(lambda: ops.conv2d_wgrad(x, dz, h, w, 3, stride))
+        fl = 2.0 * b * ho * wo * cout * cin * 9
+        msg += f" | old {t_old * 1e3:.1f} us ({fl / t_old / 1e9:.0f} TF/s)  new {t_new * 1e3:.1f} us ({fl / t_new / 1e9:.0f} TF/s)"
+    L.delora_conv_select_kernel(1)
+    print(("OK   " if ok else "FAIL ") + msg, flush=True)
+    return ok
+
+
 def main():
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     ok = True
@@ -121,6 +147,14 @@ def main():
     ok &= check_fprop(1, 64, 256, 3, 40, 3, 2, True, False)
     ok &= check_fprop(3, 128, 512, 9, 23, 3, 1, True, False)
     ok &= check_dgrad(2, 256, 128, 10, 180, (1, 2), 3, True, False)
+    ok &= check_wgrad(1, 64, 64, 8, 128, (1, 1), False)
+    ok &= check_wgrad(2, 64, 64, 6, 180, (1, 1), False)
+    ok &= check_wgrad(1, 128, 128, 8, 128, (1, 1), False)
+    ok &= check_wgrad(2, 64, 128, 16, 256, (1, 2), False)
+    ok &= check_wgrad(1, 256, 512, 16, 128, (2, 2), False)
+    ok &= check_wgrad(1, 256, 512, 64, 45, (2, 2), False)
+    ok &= check_wgrad(2, 512, 512, 32, 23, (1, 1), False)
+    ok &= check_wgrad(1, 128, 256, 64, 90, (1, 2), False)
     print(f"-- small cases done in {time.time() - t0:.1f} s, ok={ok}", flush=True)
     if not quick:
         # bench shapes (B = 16, 64x2048 image): L2 128ch @64x256, L3 256ch @64x128, L4 512ch @32x64
@@ -130,6 +164,14 @@ def main():
         check_fprop(16, 128, 128, 64, 256, 3, 3, True)
         check_dgrad(16, 128, 256, 64, 256, (1, 2), 3, True)
         check_dgrad(16, 256, 512, 64, 128, (2, 2), 3, True)
+    if not quick:
+        check_wgrad(16, 64, 64, 64, 512, (1, 1))
+        check_wgrad(16, 128, 128, 64, 256, (1, 1))
+        check_wgrad(16, 64, 128, 64, 512, (1, 2))
+        check_wgrad(16, 256, 256, 64, 128, (1, 1))
+        check_wgrad(16, 128, 256, 64, 256, (1, 2))
+        check_wgrad(16, 512, 512, 32, 64, (1, 1))
+        check_wgrad(16, 256, 512, 64, 128, (2, 2))
     print("ALL OK" if ok else "SOME FAILED", flush=True)
     return 0 if ok else 1
 
