@@ -165,6 +165,14 @@ conv_wgrad2_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_c
                     for (int j = 0; j < 8; ++j)
                         o4[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
                                             __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+                } else if (p.mode == 2) {
+                    // stem: rows = [filter row block][k = q * 16 + c], columns = output channels
+                    const int fr = mm.tap[m >> 6], k = m & 63, q = k >> 4, c = k & 15;
+                    if (fr >= 0 && q < 3) {
+                        float* o = out_split + ((size_t)(fr * 3 + q) * p.Cout + co0 + c0) * p.Cin + c;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[(size_t)j * p.Cin] = __uint_as_float(acc[j]);
+                    }
                 } else {
                     // rows = [tap block][64 input channels], columns = output channels: a warp's 32 lanes are 32
                     // consecutive input channels of one (tap, co) -> coalesced 128-byte stores
@@ -183,20 +191,40 @@ conv_wgrad2_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_c
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.acc_alloc);
 }
 
-// sum the split-K slices in a fixed order; reads coalesced along ci, writes the torch layout dW[co][ci][r][s]
+// sum the split-K slices in a fixed order (deterministic) and write the torch layout dW[co][ci][r][s].
+// blockDim = (32, 8): thread (x, y) owns 4 consecutive input channels of one (tap, co) and the slices y, y + 8, ...;
+// the 8 partial sums are combined through shared memory in y order.  Reads are 512 contiguous bytes per warp.
 __global__ void __launch_bounds__(256)
 wgrad2_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cout, int Cin, int Cin_true,
                      float* __restrict__ dw) {
-    const size_t total = (size_t)taps * Cout * Cin;
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= total) return;
-    const int ci = (int)(i % Cin);
-    const int co = (int)((i / Cin) % Cout);
-    const int tap = (int)(i / ((size_t)Cin * Cout));
-    if (ci >= Cin_true) return;
-    float acc = 0.0f;
-    for (int s = 0; s < splits; ++s) acc += __ldg(partial + (size_t)s * total + i);
-    dw[((size_t)co * Cin_true + ci) * taps + tap] = acc;
+    __shared__ float4 sm[8][32];
+    const size_t total4 = (size_t)taps * Cout * Cin / 4;
+    const size_t q = (size_t)blockIdx.x * 32 + threadIdx.x;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < total4) {
+        const float4* src = reinterpret_cast<const float4*>(partial) + q;
+        for (int s = threadIdx.y; s < splits; s += 8) {
+            const float4 v = __ldg(src + (size_t)s * total4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    sm[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && q < total4) {
+#pragma unroll
+        for (int y = 1; y < 8; ++y) {
+            const float4 v = sm[y][threadIdx.x];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const size_t i = q * 4;
+        const int ci = (int)(i % Cin);
+        const int co = (int)((i / Cin) % Cout);
+        const int tap = (int)(i / ((size_t)Cin * Cout));
+        const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (ci + j < Cin_true) dw[((size_t)co * Cin_true + ci + j) * taps + tap] = vals[j];
+    }
 }
 
 bool wgrad2_eligible(int Cin, int Cout, int ksize, int stride_h, int stride_w) {
@@ -329,8 +357,68 @@ int wgrad2_launch(const void* x, const void* dz, float* dw, float* scratch, int 
     }
     conv_wgrad2_tc_kernel<<<p.n_tiles * p.splits, kWgThreads, smem, st>>>(map_dz, map_x, scratch, p);
     DELORA_CHECK_LAUNCH("conv_wgrad2_tc_kernel");
-    const size_t total = (size_t)9 * Cout * Cin;
-    wgrad2_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(scratch, p.splits, 9, Cout, Cin, Cin_true, dw);
+    const size_t total4 = (size_t)9 * Cout * Cin / 4;
+    wgrad2_reduce_kernel<<<(unsigned)((total4 + 31) / 32), dim3(32, 8), 0, st>>>(scratch, p.splits, 9, Cout, Cin, Cin_true, dw);
+    DELORA_CHECK_LAUNCH("wgrad2_reduce_kernel");
+    return 0;
+}
+
+// stem (conv_stem.cu): X tiles come from the overlapping-stride map (one 128-byte row = the 4 x 16-channel window of
+// an output pixel), M = 128 = two filter rows x 64 k, N = 64 output channels, two MMAs per K-step
+static void wgrad2_stem_shape(int B, int H, int Wout, Wg2Params* p) {
+    p->mode = 2;
+    p->NS = 128; p->segs = (Wout + 127) / 128; p->k_rows = B * H * p->segs;
+    p->ci_per_tile = 16; p->co_per_tile = 64; p->ci_tiles = 1; p->co_tiles = 1; p->n_tiles = 1;
+    p->splits = p->k_rows < kNumSMs ? (p->k_rows > 0 ? p->k_rows : 1) : kNumSMs;
+}
+
+int64_t wgrad2_stem_scratch_floats(int B, int H, int Wout) {
+    Wg2Params p;
+    wgrad2_stem_shape(B, H, Wout, &p);
+    return (int64_t)p.splits * 9 * 64 * 16;
+}
+
+int wgrad2_launch_stem(const CUtensorMap& map_x, const void* dz, float* dw, float* scratch, int B, int H, int Wout,
+                       int Cin_true, cudaStream_t st) {
+    Wg2Params p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.Cin = 16; p.Cout = 64; p.taps = 9; p.sh = 1; p.sw = 1; p.Hout = H; p.Wout = Wout;
+    wgrad2_stem_shape(B, H, Wout, &p);
+    const int T = 16384;
+    p.loads[0] = WgLoad{0, 0, 0, 0, 0, T};
+    for (int rr = 0; rr < 3; ++rr) p.loads[1 + rr] = WgLoad{1, 0, 0, rr, T + rr * T, T};
+    const WgMma m0 = {T, 0, T, 0, 64, 0, 0, {0, 1, -1}};           // filter rows 0, 1
+    const WgMma m1 = {3 * T, 0, T, 0, 64, 64, 0, {2, -1, -1}};     // filter row 2 (+ an ignored block)
+    p.mma[0] = m0; p.mma[1] = m1;
+    p.n_loads = 4; p.n_mma = 2; p.stage_bytes = 4 * T; p.stage_tx = 4 * T; p.stages = 3; p.acc_alloc = 128;
+    PFN_cuTensorMapEncodeTiled_v12000 encode = get_tensor_map_encoder();
+    DELORA_CHECK_ARG(encode != nullptr, "stem wgrad: cuTensorMapEncodeTiled not available");
+    CUtensorMap map_dz;
+    {
+        const int Hp = H + 2, Wp = Wout + 2;
+        cuuint64_t dims[4] = {64, (cuuint64_t)(Wp - 1), (cuuint64_t)(Hp - 1), (cuuint64_t)B};
+        cuuint64_t strides[3] = {128, (cuuint64_t)Wp * 128, (cuuint64_t)Hp * Wp * 128};
+        cuuint32_t box[4] = {64, 128, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult rc = encode(&map_dz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dz), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DELORA_CHECK_ARG(rc == CUDA_SUCCESS, "stem wgrad: tensor map (dz) failed: %d", (int)rc);
+    }
+    // + one tile of slack after the last stage: the ignored second block of the last MMA reads it
+    const size_t smem = (size_t)p.stages * p.stage_bytes + T + (2 * kWgMaxStages + 1) * 8 + 16 + 1024;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {};
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        DELORA_CHECK_ARG(e == cudaSuccess, "stem wgrad: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    conv_wgrad2_tc_kernel<<<p.n_tiles * p.splits, kWgThreads, smem, st>>>(map_dz, map_x, scratch, p);
+    DELORA_CHECK_LAUNCH("conv_wgrad2_tc_kernel (stem)");
+    const size_t total4 = (size_t)9 * 64 * 16 / 4;
+    wgrad2_reduce_kernel<<<(unsigned)((total4 + 31) / 32), dim3(32, 8), 0, st>>>(scratch, p.splits, 9, 64, 16, Cin_true, dw);
     DELORA_CHECK_LAUNCH("wgrad2_reduce_kernel");
     return 0;
 }

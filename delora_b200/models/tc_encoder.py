@@ -32,9 +32,41 @@ class _EncoderTrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_pooled):
+        if ctx.state is None:
+            raise RuntimeError("tensor-core encoder: backward called twice on the same forward (saved activations "
+                               "were released); run the forward again")
         grads = ctx.enc._backward(ctx.state, g_pooled.float().contiguous())
+        ctx.state["slot"].release()
         ctx.state = None
         return (None, None, None) + tuple(grads)
+
+
+class _Slot:
+    """One set of saved-activation buffers.  A grad-enabled forward takes the lowest free slot and keeps it until its
+    backward has run (or its graph is dropped), so a second forward before the first backward -- gradient
+    accumulation, two model calls in one step, a loss pass interleaved with training -- never overwrites tensors an
+    earlier graph still needs."""
+
+    def __init__(self, index):
+        self.index, self.busy = index, False
+
+
+class _SlotLease:
+    """Held by the autograd graph of one forward; gives the slot back on backward or when the graph is dropped."""
+
+    def __init__(self, slot):
+        self.slot = slot
+        slot.busy = True
+
+    @property
+    def index(self):
+        return self.slot.index
+
+    def release(self):
+        self.slot.busy = False
+
+    def __del__(self):
+        self.slot.busy = False
 
 
 class TensorCoreEncoder:
@@ -55,7 +87,9 @@ class TensorCoreEncoder:
         # small kernel per layer whenever the fp32 parameters change (every training step; after load_state_dict)
         self._wbufs = None
         self._wversion = None
+        self._wtable = None
         self._buf = {}
+        self._slots = []
 
     def _weight_buffers(self):
         params = self.trunk_parameters()
@@ -67,16 +101,37 @@ class TensorCoreEncoder:
                 fwd = torch.empty((cout, k * k, cin_pad), dtype=torch.bfloat16, device=p_.device)
                 flip = None if i == 0 else torch.empty((cin, k * k, cout), dtype=torch.bfloat16, device=p_.device)
                 bufs.append((fwd, flip, cin_pad))
-            self._wbufs, self._wversion = bufs, None
+            # stem in the 16-channel layout of csrc/conv_stem.cu (used when the image width is even)
+            self._wstem = torch.empty((3, 64, 64), dtype=torch.bfloat16, device=params[0].device)
+            self._wbufs, self._wversion, self._wtable = bufs, None, None
         return params, self._wbufs
 
+    def _stem_fast(self, w):
+        p0 = self.model.resnet.conv1.weight
+        return w % 2 == 0 and p0.shape[0] == 64 and p0.shape[1] <= 16
+
     def _refresh_weights(self, force=False):
-        """-> list of (w_fwd, w_flip) per trunk parameter, up to date with the fp32 parameters."""
+        """-> list of (w_fwd, w_flip) per trunk parameter, up to date with the fp32 parameters: ONE launch rewrites
+        every bf16 filter copy (delora_conv_weight_prep_multi; the pointer table is rebuilt only if a parameter moved)."""
         params, bufs = self._weight_buffers()
-        version = tuple(p_._version for p_ in params) + tuple(p_.data_ptr() for p_ in params)
+        ptrs = tuple(p_.data_ptr() for p_ in params)
+        version = tuple(p_._version for p_ in params) + ptrs
         if force or version != self._wversion:
-            for p_, (fwd, flip, cin_pad) in zip(params, bufs):
-                ops.conv_weight_prep(p_, fwd, flip, cin_pad)
+            if self._wtable is None or self._wtable[1] != ptrs:
+                rows = []
+                for p_, (fwd, flip, cin_pad) in zip(params, bufs):
+                    cout, cin, k, _ = p_.shape
+                    rows.append([p_.data_ptr(), fwd.data_ptr(), flip.data_ptr() if flip is not None else 0, cout, cin, k,
+                                 cin_pad, 0])
+                p0 = params[0]
+                if p0.shape[0] == 64 and p0.shape[1] <= 16:
+                    rows.append([p0.data_ptr(), self._wstem.data_ptr(), 0, 64, p0.shape[1], 3, 16, 1])
+                table = torch.tensor(rows, dtype=torch.int64).to(params[0].device)
+                self._wtable = (table, ptrs, len(rows))
+            for p_ in params:
+                if p_.dtype != torch.float32 or not p_.is_contiguous():
+                    raise Exception("tensor-core encoder: convolution weights must be contiguous fp32")
+            ops.conv_weight_prep_multi(self._wtable[0], self._wtable[2])
             self._wversion = version
         return bufs
 
@@ -91,13 +146,21 @@ class TensorCoreEncoder:
             out.append({"w1": w1, "w2": w2, "wd": wd})
         return stem, out
 
-    def _buffer(self, tag, b, h, w, c, device):
-        key = (tag, b, h, w, c)
+    def _buffer(self, tag, b, h, w, c, device, slot=0):
+        key = (str(device), slot, tag, b, h, w, c)
         t = self._buf.get(key)
         if t is None:
             t = ops.padded_nhwc_zeros(b, h, w, c, device)      # halo rows stay zero forever
             self._buf[key] = t
         return t
+
+    def _take_slot(self):
+        for sl in self._slots:
+            if not sl.busy:
+                return _SlotLease(sl)
+        sl = _Slot(len(self._slots))
+        self._slots.append(sl)
+        return _SlotLease(sl)
 
     @torch.no_grad()
     def features(self, image_1, image_2):
@@ -105,9 +168,13 @@ class TensorCoreEncoder:
         b, _, h, w = image_1.shape
         dev = image_1.device
         stem_w, blk_w = self._block_weights(self._refresh_weights())
-        x = ops.images_to_nhwc(image_1.float().contiguous(), image_2.float().contiguous(), 64)
         w2 = ops.conv_out_size(w, 2)
-        y = ops.conv2d_fprop(x, stem_w[0], h, w, 3, (1, 2), self.act, None, self._buffer("stem", b, h, w2, 64, dev))
+        if self._stem_fast(w):
+            x = ops.images_to_nhwc16(image_1.float().contiguous(), image_2.float().contiguous())
+            y = ops.stem_fprop(x, self._wstem, h, w, self.act, self._buffer("stem", b, h, w2, 64, dev))
+        else:
+            x = ops.images_to_nhwc(image_1.float().contiguous(), image_2.float().contiguous(), 64)
+            y = ops.conv2d_fprop(x, stem_w[0], h, w, 3, (1, 2), self.act, None, self._buffer("stem", b, h, w2, 64, dev))
         w4 = w2 // 2
         cur = self._buffer("pool", b, h, w4, 64, dev)
         L = ops._lib.lib()
@@ -171,15 +238,22 @@ class TensorCoreEncoder:
         dev = image_1.device
         L = ops._lib.lib()
         it = iter(weights)
-        st = {"B": b, "H": h, "W": w, "blocks": []}
+        slot = self._take_slot()
+        sid = slot.index
+        st = {"B": b, "H": h, "W": w, "blocks": [], "slot": slot}
         w_stem = next(it)
         stem_w, blk_w = self._block_weights(self._refresh_weights(force=True))    # bf16 filters of THIS step's weights
-        st["x_in"] = ops.images_to_nhwc(image_1, image_2, 64)
         w2 = ops.conv_out_size(w, 2)
-        st["y0"] = ops.conv2d_fprop(st["x_in"], stem_w[0], h, w, 3, (1, 2), self.act, None,
-                                    self._buffer("t_stem", b, h, w2, 64, dev))
+        st["stem_fast"] = self._stem_fast(w)
+        if st["stem_fast"]:
+            st["x_in"] = ops.images_to_nhwc16(image_1, image_2)
+            st["y0"] = ops.stem_fprop(st["x_in"], self._wstem, h, w, self.act, self._buffer("t_stem", b, h, w2, 64, dev, sid))
+        else:
+            st["x_in"] = ops.images_to_nhwc(image_1, image_2, 64)
+            st["y0"] = ops.conv2d_fprop(st["x_in"], stem_w[0], h, w, 3, (1, 2), self.act, None,
+                                        self._buffer("t_stem", b, h, w2, 64, dev, sid))
         w4 = w2 // 2
-        st["p0"] = self._buffer("t_pool", b, h, w4, 64, dev)
+        st["p0"] = self._buffer("t_pool", b, h, w4, 64, dev, sid)
         st["idx"] = torch.empty((b, h, w4, 64), dtype=torch.uint8, device=dev)
         ops._lib.check(L.delora_maxpool_w_idx_nhwc_bf16(st["y0"].data_ptr(), b, h, w2, 64, st["p0"].data_ptr(),
                                                         st["idx"].data_ptr(), ops._stream()),
@@ -192,14 +266,14 @@ class TensorCoreEncoder:
             sh, sw = blk["stride"]
             oh, ow, co = ops.conv_out_size(ch, sh), ops.conv_out_size(cw, sw), blk["cout"]
             t1 = ops.conv2d_fprop(cur, bw["w1"][0], ch, cw, 3, (sh, sw), self.act, None,
-                                  self._buffer(f"t{i}a", b, oh, ow, co, dev))
+                                  self._buffer(f"t{i}a", b, oh, ow, co, dev, sid))
             if wd is not None:
                 ident = ops.conv2d_fprop(cur, bw["wd"][0], ch, cw, 1, (sh, sw), ops.ACT_NONE, None,
-                                         self._buffer(f"t{i}d", b, oh, ow, co, dev))
+                                         self._buffer(f"t{i}d", b, oh, ow, co, dev, sid))
             else:
                 ident = cur
             out = ops.conv2d_fprop(t1, bw["w2"][0], oh, ow, 3, (1, 1), self.act, ident,
-                                   self._buffer(f"t{i}o", b, oh, ow, co, dev))
+                                   self._buffer(f"t{i}o", b, oh, ow, co, dev, sid))
             st["blocks"].append({"x": cur, "t1": t1, "out": out, "w1": w1, "w2": wc2, "wd": wd, "stride": (sh, sw),
                                  "f1": bw["w1"][1], "f2": bw["w2"][1], "fd": bw["wd"][1] if bw["wd"] is not None else None,
                                  "in_hw": (ch, cw), "out_hw": (oh, ow)})
@@ -264,7 +338,10 @@ class TensorCoreEncoder:
         ops._lib.check(L.delora_maxpool_w_bwd_nhwc_bf16(d_pool.data_ptr(), st["idx"].data_ptr(), st["y0"].data_ptr(), b, h,
                                                         w2, 64, act_id, dz0.data_ptr(), ops._stream()),
                        "delora_maxpool_w_bwd_nhwc_bf16")
-        g_stem = ops.conv2d_wgrad(st["x_in"], dz0, h, w, 3, (1, 2), cin_true=st["w_stem"].shape[1])
+        if st["stem_fast"]:
+            g_stem = ops.stem_wgrad(st["x_in"], dz0, h, w, st["w_stem"].shape[1])
+        else:
+            g_stem = ops.conv2d_wgrad(st["x_in"], dz0, h, w, 3, (1, 2), cin_true=st["w_stem"].shape[1])
         grads = [g_stem]
         for g_w1, g_w2, g_wd in reversed(grads_rev):
             grads += [g_w1, g_w2]

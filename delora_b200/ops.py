@@ -391,3 +391,56 @@ def nhwc_to_nchw(x, h, w):
     _lib.check(L.delora_nhwc_to_nchw_f32(_req(x, torch.bfloat16, "x"), b, h, w, c, y.data_ptr(), _stream()),
                "delora_nhwc_to_nchw_f32")
     return y
+
+
+# ---- stem on the 16-channel layout (csrc/conv_stem.cu)
+def images_to_nhwc16(image_1, image_2):
+    b, _, h, w = image_1.shape
+    x = torch.empty((b, h + 2, w + 2, 16), dtype=torch.bfloat16, device=image_1.device)
+    L = _lib.lib()
+    _lib.check(L.delora_images_to_nhwc16_bf16(_req(image_1, torch.float32, "image_1"),
+                                              _req(image_2, torch.float32, "image_2"), b, h, w, x.data_ptr(), _stream()),
+               "delora_images_to_nhwc16_bf16")
+    return x
+
+
+def stem_weight_prep(weight, w_stem):
+    """weight [64,Cin<=16,3,3] fp32 -> w_stem [3,64,64] bf16 in place."""
+    L = _lib.lib()
+    _lib.check(L.delora_stem_weight_prep_bf16(_req(weight.detach(), torch.float32, "weight"), weight.shape[1],
+                                              w_stem.data_ptr(), _stream()), "delora_stem_weight_prep_bf16")
+    return w_stem
+
+
+def stem_fprop(x16, w_stem, h, w, act, out=None):
+    """x16 [B,H+2,W+2,16], w_stem [3,64,64] -> y [B,H+2,W/2+2,64] (3x3, stride (1,2), activation)."""
+    b = x16.shape[0]
+    if out is None:
+        out = padded_nhwc_zeros(b, h, w // 2, 64, x16.device)
+    L = _lib.lib()
+    _lib.check(L.delora_stem_fprop_bf16(_req(x16, torch.bfloat16, "x16"), _req(w_stem, torch.bfloat16, "w_stem"),
+                                        out.data_ptr(), b, h, w, int(act), _stream()), "delora_stem_fprop_bf16")
+    return out
+
+
+def stem_wgrad(x16, dz, h, w, cin_true):
+    """-> dW [64, cin_true, 3, 3] fp32."""
+    b = x16.shape[0]
+    L = _lib.lib()
+    n = int(L.delora_stem_wgrad_scratch_floats(b, h, w))
+    key = (x16.device.index, n)
+    scratch = _wgrad_scratch.get(key)
+    if scratch is None:
+        scratch = torch.empty((n,), dtype=torch.float32, device=x16.device)
+        _wgrad_scratch[key] = scratch
+    dw = torch.empty((64, cin_true, 3, 3), dtype=torch.float32, device=x16.device)
+    _lib.check(L.delora_stem_wgrad_bf16(_req(x16, torch.bfloat16, "x16"), _req(dz, torch.bfloat16, "dz"), dw.data_ptr(),
+                                        scratch.data_ptr(), b, h, w, int(cin_true), _stream()), "delora_stem_wgrad_bf16")
+    return dw
+
+
+def conv_weight_prep_multi(table, n_layers):
+    """table: int64 CUDA tensor [n_layers, 8] (see include/delora_b200.h)."""
+    L = _lib.lib()
+    _lib.check(L.delora_conv_weight_prep_multi(_req(table, torch.int64, "table"), int(n_layers), _stream()),
+               "delora_conv_weight_prep_multi")

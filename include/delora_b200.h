@@ -281,6 +281,24 @@ int delora_zero_upsample_nhwc_bf16(const void* x, int B, int H, int W, int C, in
 int delora_conv_weight_prep_bf16(const float* w, int Cout, int Cin, int ksize, int Cin_pad, void* w_fwd, void* w_flip,
                                  void* stream);
 
+/* All encoder filters in one launch (replaces 20 delora_conv_weight_prep_bf16 calls per training step).
+ * table: device array of n_layers x 8 int64 = {fp32 weight ptr, w_fwd ptr, w_flip ptr or 0, Cout, Cin, k, Cin_pad, kind};
+ * kind 0 = the layouts of delora_conv_weight_prep_bf16, kind 1 = the stem layout of delora_stem_weight_prep_bf16. */
+int delora_conv_weight_prep_multi(const void* table, int n_layers, void* stream);
+
+/* ---- Encoder stem (src/models/resnet_modified.py:40 conv1: 3x3, stride (1,2), 8 -> 64 channels, + activation :99) on a
+ * 16-channel input layout; replaces the channel-padded (8 -> 64) route through delora_conv2d_fprop/wgrad_bf16.
+ * x16    [B, H+2, W+2, 16] bf16: channels 0..7 = cat(image_1, image_2) (src/models/model.py:98), 8..15 zero, padding
+ *        materialised as everywhere (delora_images_to_nhwc16_bf16 writes it)
+ * w_stem [3, 64, 64] bf16: [filter row][output channel][k = q * 16 + c] (delora_stem_weight_prep_bf16)
+ * y      [B, H+2, W/2+2, 64] bf16 out;  dz same shape;  dw [64, Cin_true, 3, 3] fp32.  W must be even. */
+int delora_images_to_nhwc16_bf16(const float* image_1, const float* image_2, int B, int H, int W, void* x16, void* stream);
+int delora_stem_weight_prep_bf16(const float* w, int Cin, void* w_stem, void* stream);
+int delora_stem_fprop_bf16(const void* x16, const void* w_stem, void* y, int B, int H, int W, int act, void* stream);
+int64_t delora_stem_wgrad_scratch_floats(int B, int H, int W);
+int delora_stem_wgrad_bf16(const void* x16, const void* dz, float* dw, float* scratch, int B, int H, int W, int Cin_true,
+                           void* stream);
+
 /* cat(image_1, image_2) ([B,4,H,W] fp32 each, src/models/model.py:98) -> [B,H+2,W+2,Cpad] bf16 padded NHWC */
 int delora_images_to_nhwc_bf16(const float* image_1, const float* image_2, int B, int H, int W, int Cpad,
                                void* x, void* stream);

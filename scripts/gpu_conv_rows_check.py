@@ -128,6 +128,45 @@ def check_wgrad(b, cin, cout, h, w, stride, time_it=True):
     return ok
 
 
+def check_stem(b, h, w, time_it=True):
+    import torch.nn.functional as F
+    gen = torch.Generator(device=DEV).manual_seed(h + w)
+    img1 = torch.randn(b, 4, h, w, device=DEV, generator=gen) * 5.0
+    img2 = torch.randn(b, 4, h, w, device=DEV, generator=gen) * 5.0
+    wt = torch.randn(64, 8, 3, 3, device=DEV, generator=gen) / 72 ** 0.5
+    x16 = ops.images_to_nhwc16(img1, img2)
+    wst = torch.empty((3, 64, 64), dtype=torch.bfloat16, device=DEV)
+    ops.stem_weight_prep(wt, wst)
+    y = ops.stem_fprop(x16, wst, h, w, ops.ACT_TANH)
+    x = torch.cat([img1, img2], 1).to(torch.bfloat16).float()
+    ref = torch.tanh(F.conv2d(F.pad(x, (1, 1, 0, 0), mode="circular"), wt.to(torch.bfloat16).float(), stride=(1, 2), padding=(1, 0)))
+    got = ops.nhwc_to_nchw(y, h, w // 2)
+    e1 = (got - ref).abs().max().item()
+    yf = y.float()
+    halo_ok = torch.equal(yf[:, 1:-1, 0], yf[:, 1:-1, w // 2]) and torch.equal(yf[:, 1:-1, w // 2 + 1], yf[:, 1:-1, 1])
+    # wgrad vs autograd
+    xr = x.clone().requires_grad_(False)
+    wr = wt.to(torch.bfloat16).float().requires_grad_(True)
+    dz = (torch.randn(b, 64, h, w // 2, device=DEV, generator=gen) * 0.5).to(torch.bfloat16).float()
+    F.conv2d(F.pad(xr, (1, 1, 0, 0), mode="circular"), wr, stride=(1, 2), padding=(1, 0)).backward(dz)
+    dzp = ops.padded_nhwc_zeros(b, h, w // 2, 64, DEV)
+    dzp[:, 1:h + 1, 1:w // 2 + 1] = dz.permute(0, 2, 3, 1).to(torch.bfloat16)
+    dzp[:, 1:h + 1, 0] = dzp[:, 1:h + 1, w // 2]
+    dzp[:, 1:h + 1, w // 2 + 1] = dzp[:, 1:h + 1, 1]
+    dw = ops.stem_wgrad(x16, dzp, h, w, 8)
+    e2 = (dw - wr.grad).abs().max().item() / wr.grad.abs().max().item()
+    ok = e1 < 8e-3 and halo_ok and e2 < 1e-3
+    msg = f"stem B{b} {h}x{w}: fprop maxerr {e1:.4g} halo {halo_ok} wgrad rel {e2:.3g}"
+    if time_it:
+        out = ops.padded_nhwc_zeros(b, h, w // 2, 64, DEV)
+        t_f = timed(lambda: ops.stem_fprop(x16, wst, h, w, ops.ACT_TANH, out))
+        t_w = timed(lambda: ops.stem_wgrad(x16, dzp, h, w, 8))
+        t_i = timed(lambda: ops.images_to_nhwc16(img1, img2))
+        msg += f" | to_nhwc16 {t_i * 1e3:.1f} us  fprop {t_f * 1e3:.1f} us  wgrad {t_w * 1e3:.1f} us"
+    print(("OK   " if ok else "FAIL ") + msg, flush=True)
+    return ok
+
+
 def main():
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     ok = True
@@ -155,6 +194,9 @@ def main():
     ok &= check_wgrad(1, 256, 512, 64, 45, (2, 2), False)
     ok &= check_wgrad(2, 512, 512, 32, 23, (1, 1), False)
     ok &= check_wgrad(1, 128, 256, 64, 90, (1, 2), False)
+    ok &= check_stem(1, 8, 256, False)
+    ok &= check_stem(2, 16, 180, False)
+    ok &= check_stem(1, 64, 720, False)
     print(f"-- small cases done in {time.time() - t0:.1f} s, ok={ok}", flush=True)
     if not quick:
         # bench shapes (B = 16, 64x2048 image): L2 128ch @64x256, L3 256ch @64x128, L4 512ch @32x64
@@ -165,6 +207,7 @@ def main():
         check_dgrad(16, 128, 256, 64, 256, (1, 2), 3, True)
         check_dgrad(16, 256, 512, 64, 128, (2, 2), 3, True)
     if not quick:
+        check_stem(16, 64, 2048)
         check_wgrad(16, 64, 64, 64, 512, (1, 1))
         check_wgrad(16, 128, 128, 64, 256, (1, 1))
         check_wgrad(16, 64, 128, 64, 512, (1, 2))
