@@ -15,6 +15,10 @@ forward and backward to the 3x4 transform, for the whole batch.
                 the compute stream) and D2H of the losses + transform gradients.
 * `roofline`  : dominant kernel (by measured time inside the timed region), algorithmic bytes /
                 its measured duration against the measured HBM peak (MEASURED_PEAKS.json).
+* `roofline_encoder`: the tcgen05 encoder (fprop + dgrad + wgrad) timed alone against the measured sustained bf16 peak.
+* `ts` / `train_step` / `train_scaling`: BASELINE configs[2] / configs[3], the full training step (batch 16 per GPU)
+                with the gradient all-reduce overlapped with the backward; `ar_exposed_ms` = step - step without the
+                collective; `cudnn_fp32_ms` / `cudnn_bf16_ms` = the reference's nn.Conv2d stack on the same box (N = 1).
 * `cpu_baseline` / `--impl reference`: the oracle port of the reference's CPU path
                 (oracle/delora_oracle.py: torch-CPU + numpy + scipy cKDTree) on the host cores.
 Multi-GPU: one process per GPU (torchrun), pairs sharded across ranks, no data-path collective
@@ -52,6 +56,22 @@ def measured_peaks():
             p = json.load(f)
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_bf16_peak():
+    """Sustained bf16 TFLOP/s (a kernel timed inside a long step): MEASURED_PEAKS.json, else the guide's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        if "bf16_tflops_sustained" in p:
+            return float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+
+
+# fp32 work of the normals kernel per pixel: 77 taps x (3 sub + 1 gate test + 1 count + 3 sums + 6 second moments = 28 flops,
+# FMAs counted as 2) + ~250 for the 3x3 Jacobi eigen-solve, orientation and gates (SURVEY.md 8(d): H*W*(77*~30 + ~250))
+NORMALS_FLOP_PER_PIXEL = 77 * 30 + 250
 
 
 class ClockSampler(threading.Thread):
@@ -188,6 +208,98 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def train_leg(args, rank, world, device, raw, n_max):
+    """BASELINE configs[2] (1 GPU) / configs[3] (DDP, 16 pairs per GPU): projection + normals + tcgen05 encoder fwd/bwd +
+    heads + fused ICP loss + gradient all-reduce (overlapped, parallel_grad.py) + Adam; CUDA events, max over ranks.
+    Also measured here, on the same inputs: the step without the collective (-> exposed all-reduce time), the blocking
+    flat all-reduce, the encoder alone (-> tensor-core roofline) and, on rank 0 at N = 1, the reference's own
+    nn.Conv2d stack on cuDNN in fp32 and under bf16 autocast (BASELINE.md §3 'reference on the same box')."""
+    from delora_b200 import synthetic
+    from delora_b200.train_step import SyntheticTrainStep
+    tcfg = synthetic.fov_config(h=H, w=W, device=device)
+    tb = args.train_batch
+    tpts = torch.zeros((2 * tb, 3, n_max), dtype=torch.float32)
+    tcnt = torch.zeros((2 * tb,), dtype=torch.int32)
+    for i in range(tb):
+        s1, s2, _, _ = raw[i % len(raw)]
+        tpts[i, :, :s1.shape[1]] = s1
+        tpts[tb + i, :, :s2.shape[1]] = s2
+        tcnt[i], tcnt[tb + i] = s1.shape[1], s2.shape[1]
+    tpts, tcnt = tpts.to(device), tcnt.to(device)
+
+    def timed(ts, steps):
+        for _ in range(3):
+            ts.step()
+        torch.cuda.synchronize()
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss, _ = ts.step()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        return max_over_ranks(e0.elapsed_time(e1), world, device) / steps, float(loss)
+
+    def build(**kw):
+        torch.manual_seed(1234)
+        ts = SyntheticTrainStep(tcfg, tb, n_max, **kw)
+        ts.load(tpts, tcnt)
+        return ts
+
+    ts = build(use_tensor_cores=True, grad_sync="bucketed")
+    ms, loss = timed(ts, args.train_steps)
+    out = {"ms_per_step": ms, "pairs_per_s": world * tb / (ms * 1e-3), "n_gpus": world, "batch_per_gpu": tb,
+           "loss": loss, "encoder_gflop_per_step": 3 * 96.17 * tb,
+           "workload": f"full training step, batch {tb}/GPU, 64x{W}: projection + normals + tcgen05 encoder fwd/bwd "
+                       "(bf16) + heads + fused ICP loss fwd/bwd (fp32) + Adam"
+                       + (" + bucketed NCCL all-reduce of 11.88 M fp32 gradients overlapped with the backward"
+                          if world > 1 else "")}
+    if world == 1:
+        # encoder alone: forward + backward of the trunk on fixed images -> achieved bf16 TFLOP/s vs the measured peak
+        enc = ts.model._tensor_core_path()
+        with torch.no_grad():
+            from delora_b200 import ops
+            image, _ = ops.project(ts.points, ts.n_points, H, W, ts.hf, ts.vf)
+        img1, img2 = image[:tb].contiguous(), image[tb:].contiguous()
+        sel = torch.randn(tb, 512, device=device)
+
+        def enc_step():
+            ts.optimizer.zero_grad(set_to_none=True)
+            (enc.pooled_features(img1, img2) * sel).sum().backward()
+            ts.sync.finish()
+        for _ in range(2):
+            enc_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.train_steps):
+            enc_step()
+        e1.record()
+        torch.cuda.synchronize()
+        out["encoder_ms"] = e0.elapsed_time(e1) / args.train_steps
+        del enc
+    del ts
+    if world > 1:
+        ts = build(use_tensor_cores=True, grad_sync="none")
+        ms_none, _ = timed(ts, args.train_steps)
+        del ts
+        ts = build(use_tensor_cores=True, grad_sync="flat")
+        ms_flat, _ = timed(ts, args.train_steps)
+        del ts
+        out.update({"ms_without_allreduce": ms_none, "allreduce_exposed_ms": ms - ms_none,
+                    "ms_blocking_flat_allreduce": ms_flat})
+    elif rank == 0 and args.cudnn_steps > 0:
+        ts = build(use_tensor_cores=False)
+        out["cudnn_fp32_ms"], _ = timed(ts, args.cudnn_steps)
+        del ts
+        ts = build(use_tensor_cores=False, autocast_bf16=True)
+        out["cudnn_bf16_ms"], _ = timed(ts, args.cudnn_steps)
+        del ts
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
@@ -279,42 +391,12 @@ def run_ours(args):
     d2h_bytes = sum(t.numel() * t.element_size() for t in out_host[0])
     assert abs(out_host[0][0][0, 1].item() - losses0[1]) <= 1e-6 * abs(losses0[1]) + 1e-12
 
-    # ---------------- full training step (BASELINE configs[2]/[3] shape), informational ----------------
+    # ---------------- full training step (BASELINE configs[2]/[3]: batch 16 per GPU, bf16 tensor-core encoder) ----
     train = None
     if args.train_steps > 0:
         try:
-            from delora_b200.train_step import SyntheticTrainStep
-            tcfg = synthetic.fov_config(h=H, w=W, device=device)
-            tb = args.train_batch
-            tpts = torch.zeros((2 * tb, 3, n_max), dtype=torch.float32)
-            tcnt = torch.zeros((2 * tb,), dtype=torch.int32)
-            for i in range(tb):
-                s1, s2, _, _ = raw[i % len(raw)]
-                tpts[i, :, :s1.shape[1]] = s1
-                tpts[tb + i, :, :s2.shape[1]] = s2
-                tcnt[i], tcnt[tb + i] = s1.shape[1], s2.shape[1]
-            torch.manual_seed(1234)
-            ts = SyntheticTrainStep(tcfg, tb, n_max, use_tensor_cores=True)
-            ts.load(tpts.to(device), tcnt.to(device))
-            for _ in range(3):
-                ts.step()
-            torch.cuda.synchronize()
-            barrier(world)
-            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0e.record()
-            for _ in range(args.train_steps):
-                tloss, _ = ts.step()
-            t1e.record()
-            torch.cuda.synchronize()
-            barrier(world)
-            tms = max_over_ranks(t0e.elapsed_time(t1e), world, device) / args.train_steps
-            train = {"workload": f"full training step, batch {tb}/GPU, 64x{W}: projection + normals + tcgen05 encoder "
-                                 "fwd/bwd (bf16) + heads + fused ICP loss fwd/bwd (fp32) + Adam"
-                                 + (" + flat NCCL gradient all-reduce (11.88 M fp32)" if world > 1 else ""),
-                     "ms_per_step": tms, "pairs_per_s": world * tb / (tms * 1e-3), "loss": float(tloss),
-                     "encoder_gflop_per_step": 3 * 96.17 * tb}
-            del ts
-        except Exception as e:                      # informational leg: never takes the headline down
+            train = train_leg(args, rank, world, device, raw, n_max)
+        except Exception as e:                      # second leg: never takes the headline down
             train = {"error": repr(e)[:300]}
 
     # ---------------- streaming inference (BASELINE configs[4]), informational, rank 0 only ----------------
@@ -386,14 +468,42 @@ def run_ours(args):
             if name in kernels and wi:
                 kernels[name]["warp_instructions"] = wi
                 kernels[name]["issue_slot_frac"] = wi / (kernels[name]["ms"] * 1e-3 * 148 * 4 * sm_clock)
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic,
-                "peak_source": peak_src,
-                "issue_slot_frac": kernels[dom].get("issue_slot_frac"),
-                "note": "algorithmic bytes (SURVEY 8(d) formulas at the measured mean K valid pixels/scan) / "
-                        "CUDA-event duration inside the timed region; see `kernels` for every operator. All three "
-                        "operators are bound by instruction issue / the FP32 pipe, not by HBM (DESIGN.md 4.1-4.3): "
-                        "`issue_slot_frac` is the fraction of the SMs' issue slots the operator's warp instructions fill"}
+    sm_clock_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    fp32_peak_tflops = 148 * 128 * 2 * sm_clock_hz / 1e12                 # FFMA lanes x 2 flops at the clock sampled under load
+    if dom == "normals":
+        # the dominant kernel is bound by the FP32 pipe, not by HBM: the roofline is
+        # its fp32 work over the fp32 peak; the HBM figure stays as a note
+        flops = 2 * PAIRS_PER_GPU * H * W * NORMALS_FLOP_PER_PIXEL
+        ach = flops / (op_ms[dom] * 1e-3) / 1e12
+        roofline = {"kernel": dom, "bound": "fp32", "achieved": ach, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                    "frac": ach / fp32_peak_tflops, "traffic": traffic,
+                    "peak_source": f"148 SMs x 128 FMA lanes x 2 x {sm_clock_hz / 1e6:.0f} MHz (SM clock sampled during the run)",
+                    "flops_per_launch": flops,
+                    "hbm": {"achieved_gbs": kernels[dom]["achieved_gbs"], "peak_gbs": peak, "frac": kernels[dom]["frac_of_hbm_peak"],
+                            "peak_source": peak_src},
+                    "issue_slot_frac": kernels[dom].get("issue_slot_frac"),
+                    "counters_measured_at": (tdoc.get("_measured_at") if traffic is not None else None),
+                    "note": "fp32 flops (SURVEY 8(d): 77 taps x ~30 + ~250 per pixel) / CUDA-event duration inside the timed "
+                            "region; `hbm` = algorithmic bytes over the measured copy bandwidth for the same launch; "
+                            "`issue_slot_frac` / `traffic` come from the ncu capture of the commit named in counters_measured_at"}
+    else:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic,
+                    "peak_source": peak_src, "issue_slot_frac": kernels[dom].get("issue_slot_frac"),
+                    "counters_measured_at": (tdoc.get("_measured_at") if traffic is not None else None),
+                    "note": "algorithmic bytes (SURVEY 8(d) formulas at the measured mean K valid pixels/scan) / "
+                            "CUDA-event duration inside the timed region; see `kernels` for every operator"}
+    roofline_encoder = None
+    if train and "encoder_ms" in train:
+        bf_peak, bf_src = measured_bf16_peak()
+        ach = train["encoder_gflop_per_step"] / train["encoder_ms"]            # GFLOP / ms = TFLOP/s
+        step_ach = train["encoder_gflop_per_step"] / train["ms_per_step"]
+        roofline_encoder = {"bound": "tensor", "achieved": ach, "peak": bf_peak, "unit": "TFLOP/s", "frac": ach / bf_peak,
+                            "peak_source": bf_src, "ms": train["encoder_ms"],
+                            "over_whole_step": {"achieved": step_ach, "frac": step_ach / bf_peak, "ms": train["ms_per_step"]},
+                            "note": "encoder forward + backward (20 convolutions: fprop, dgrad, wgrad; 3 x 96.17 GFLOP per "
+                                    "sample) timed alone with CUDA events; `over_whole_step` divides the same flops by the "
+                                    "full training step (projection, normals, loss, heads, Adam included)"}
 
     # ---------------- CPU baseline: oracle port on a bounded sample --------------------------
     cores = cpu_threads()
@@ -408,10 +518,17 @@ def run_ours(args):
         cpu_dt = time.perf_counter() - t0
         cpu_value = cpu_n / cpu_dt
 
+    tshort = None
+    if train and "ms_per_step" in train:
+        # BASELINE configs[2] / configs[3] in short keys (kept at the front AND repeated as the last key of the line so
+        # that a truncated record still carries them): ms per step, whole-job pairs/s, exposed all-reduce time
+        tshort = {"n": world, "ms": round(train["ms_per_step"], 4), "pairs_per_s": round(train["pairs_per_s"], 1),
+                  "ar_exposed_ms": (round(train["allreduce_exposed_ms"], 4) if "allreduce_exposed_ms" in train else None),
+                  "enc_frac_of_bf16_peak": (round(roofline_encoder["frac"], 4) if roofline_encoder else None)}
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f32", "data": "synthetic", "ts": tshort,
         "config": {"workload": "BASELINE configs[1]: batch=8 synthetic 64x2048 clouds per GPU, "
                                "projection+normals+point-to-plane/plane-to-plane loss fwd/bwd",
                    "pairs_per_gpu": PAIRS_PER_GPU, "H": H, "W": W, "points_per_scan": n_max,
@@ -426,7 +543,7 @@ def run_ours(args):
                 "bound": "host link: the raw fp32 scans (12 B/point) cross PCIe every step; when h2d_gbs is ~50 the "
                          "copy, not the kernels, sets this number"},
         "gpu_launches": K * pipes[0].launches_per_step,
-        "roofline": roofline, "kernels": kernels,
+        "roofline": roofline, "roofline_encoder": roofline_encoder, "kernels": kernels,
         "cpu_baseline": {"value": cpu_value, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"{cpu_n} pairs at 64x2048 through oracle.pair_forward_backward "
                                    f"(torch {torch.__version__} CPU + scipy cKDTree), {cores} of {os.cpu_count()} host threads "
@@ -436,6 +553,7 @@ def run_ours(args):
         "clocks": clocks, "wall_s_timed_region": t_wall,
         "check": {"loss_po2pl": losses0[1], "loss_pl2pl": losses0[2], "pairs": losses0[3],
                   "cpu_loss_po2pl": out["loss_po2pl"], "cpu_loss_pl2pl": out["loss_pl2pl"]},
+        "train_scaling": tshort,
     }
     print(json.dumps(line))
     if world > 1:
@@ -453,7 +571,9 @@ def main():
                     help="--impl reference: wall-clock budget of the timed CPU steps (a pair costs seconds)")
     ap.add_argument("--stream-frames", type=int, default=200,
                     help="frames of the informational streaming-inference leg (0 = skip)")
-    ap.add_argument("--train-steps", type=int, default=5, help="steps of the informational full-training-step leg (0 = skip)")
+    ap.add_argument("--train-steps", type=int, default=10, help="steps of the full-training-step leg (0 = skip)")
+    ap.add_argument("--cudnn-steps", type=int, default=3,
+                    help="steps of the reference-on-GPU bar (torch nn.Conv2d / cuDNN, fp32 and bf16 autocast; N = 1; 0 = skip)")
     ap.add_argument("--train-batch", type=int, default=16)
     ap.add_argument("--rotate", type=int, default=ROTATE, help="rotating input sets (1 only for profiling runs)")
     args = ap.parse_args()

@@ -2,6 +2,10 @@
 // (reference: src/models/resnet_modified.py:40 `self.conv1`, used at :97-99; the 8 input channels are
 // cat(image_1, image_2), src/models/model.py:98).
 //
+// Input precision: the range images hold metres (up to ~100): a single bf16 would quantise them to 0.25-0.5 m steps.  The
+// 8 spare channels carry the rounding residual: channel c = bf16(x), channel c + 8 = bf16(x - bf16(x)), both multiplied
+// by the same filter weight, so the stem sees the input with ~16 mantissa bits at no extra tensor-core work.
+//
 // Round 1 ran this layer through the generic kernel with the 8 channels padded to 64: K = 9 taps x 64 = 576 for 72
 // real products per output (8x wasted MMAs, 277 MB input tensor).  Here the input is stored with 16 channels
 // [B, H+2, W+2, 16] bf16 (8 real + 8 zero, 32 B per pixel) and ONE tensor-map row gives, for output pixel wo and filter
@@ -133,8 +137,8 @@ stem_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
-// two [B,4,H,W] fp32 range images -> [B, H+2, W+2, 16] bf16: channels 0..7 = cat(image_1, image_2)
-// (src/models/model.py:98), 8..15 zero; circular halo columns, zero halo rows.  One thread per padded pixel.
+// two [B,4,H,W] fp32 range images -> [B, H+2, W+2, 16] bf16: channels 0..7 = bf16(cat(image_1, image_2))
+// (src/models/model.py:98), 8..15 = bf16 of the rounding residual; circular halo columns, zero halo rows.
 __global__ void __launch_bounds__(256)
 images_to_nhwc16_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int B, int H, int W,
                         __nv_bfloat16* __restrict__ x) {
@@ -143,23 +147,28 @@ images_to_nhwc16_kernel(const float* __restrict__ img1, const float* __restrict_
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= total) return;
     const int wp = (int)(i % Wp), hp = (int)((i / Wp) % Hp), b = (int)(i / ((size_t)Wp * Hp));
-    uint4 lo = make_uint4(0u, 0u, 0u, 0u);
+    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi_part = make_uint4(0u, 0u, 0u, 0u);
     if (hp != 0 && hp != Hp - 1) {
         int w = wp - 1;
         if (w < 0) w = W - 1;
         if (w >= W) w = 0;
         const int h = hp - 1;
         const size_t base = ((size_t)b * 4 * H + h) * W + w, plane = (size_t)H * W;
-        __nv_bfloat162 v[4];
-        v[0] = __floats2bfloat162_rn(__ldg(img1 + base), __ldg(img1 + base + plane));
-        v[1] = __floats2bfloat162_rn(__ldg(img1 + base + 2 * plane), __ldg(img1 + base + 3 * plane));
-        v[2] = __floats2bfloat162_rn(__ldg(img2 + base), __ldg(img2 + base + plane));
-        v[3] = __floats2bfloat162_rn(__ldg(img2 + base + 2 * plane), __ldg(img2 + base + 3 * plane));
-        lo = *reinterpret_cast<uint4*>(v);
+        float f[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { f[c] = __ldg(img1 + base + c * plane); f[4 + c] = __ldg(img2 + base + c * plane); }
+        __nv_bfloat16 hv[8], lv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            hv[c] = __float2bfloat16_rn(f[c]);
+            lv[c] = __float2bfloat16_rn(f[c] - __bfloat162float(hv[c]));     // rounding residual (exact difference)
+        }
+        lo = *reinterpret_cast<uint4*>(hv);
+        hi_part = *reinterpret_cast<uint4*>(lv);
     }
     uint4* dst = reinterpret_cast<uint4*>(x + i * 16);
     dst[0] = lo;
-    dst[1] = make_uint4(0u, 0u, 0u, 0u);
+    dst[1] = hi_part;
 }
 
 // fp32 stem filter [64, 8, 3, 3] -> bf16 [3 rows][64 co][64 k], k = q * 16 + c (q < 3, c < 8), zero elsewhere
@@ -169,7 +178,8 @@ stem_weight_prep_kernel(const float* __restrict__ w, int Cin, __nv_bfloat16* __r
     if (i >= 3 * 64 * 64) return;
     const int k = i & 63, co = (i >> 6) & 63, r = i >> 12;
     const int q = k >> 4, c = k & 15;
-    const float v = (q < 3 && c < Cin) ? __ldg(w + ((size_t)co * Cin + c) * 9 + r * 3 + q) : 0.0f;
+    const int cr = c & 7;                                 // channels 8..15 (input residuals) reuse the weights of 0..7
+    const float v = (q < 3 && cr < Cin) ? __ldg(w + ((size_t)co * Cin + cr) * 9 + r * 3 + q) : 0.0f;
     w_stem[i] = __float2bfloat16_rn(v);
 }
 
@@ -188,7 +198,8 @@ weight_prep_multi_kernel(const long long* __restrict__ table) {
         for (int i = blockIdx.x * 256 + threadIdx.x; i < 3 * 64 * 64; i += gridDim.x * 256) {
             const int kk = i & 63, co = (i >> 6) & 63, r = i >> 12;
             const int q = kk >> 4, c = kk & 15;
-            w_fwd[i] = __float2bfloat16_rn((q < 3 && c < Cin) ? __ldg(w + ((size_t)co * Cin + c) * 9 + r * 3 + q) : 0.0f);
+            const int cr = c & 7;
+            w_fwd[i] = __float2bfloat16_rn((q < 3 && cr < Cin) ? __ldg(w + ((size_t)co * Cin + cr) * 9 + r * 3 + q) : 0.0f);
         }
         return;
     }
@@ -238,7 +249,7 @@ extern "C" int delora_images_to_nhwc16_bf16(const float* image_1, const float* i
 }
 
 extern "C" int delora_stem_weight_prep_bf16(const float* w, int Cin, void* w_stem, void* stream) {
-    DELORA_CHECK_ARG(w && w_stem && Cin >= 1 && Cin <= 16, "delora_stem_weight_prep_bf16: bad argument");
+    DELORA_CHECK_ARG(w && w_stem && Cin >= 1 && Cin <= 8, "delora_stem_weight_prep_bf16: bad argument");
     stem_weight_prep_kernel<<<(3 * 64 * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cin, (__nv_bfloat16*)w_stem);
     DELORA_CHECK_LAUNCH("stem_weight_prep_kernel");
     return 0;
@@ -291,7 +302,7 @@ extern "C" int64_t delora_stem_wgrad_scratch_floats(int B, int H, int W) { retur
 extern "C" int delora_stem_wgrad_bf16(const void* x16, const void* dz, float* dw, float* scratch, int B, int H, int W,
                                       int Cin_true, void* stream) {
     DELORA_CHECK_ARG(x16 && dz && dw && scratch, "delora_stem_wgrad_bf16: null pointer");
-    DELORA_CHECK_ARG(W % 2 == 0 && W >= 2 && Cin_true >= 1 && Cin_true <= 16, "delora_stem_wgrad_bf16: bad shape");
+    DELORA_CHECK_ARG(W % 2 == 0 && W >= 2 && Cin_true >= 1 && Cin_true <= 8, "delora_stem_wgrad_bf16: bad shape");
     CUtensorMap mx;
     DELORA_CHECK_ARG(stem_encode_x_map(&mx, x16, B, H, W, 128) == 0, "delora_stem_wgrad_bf16: tensor map (x) failed");
     return wgrad2_launch_stem(mx, dz, dw, scratch, B, H, W / 2, Cin_true, (cudaStream_t)stream);

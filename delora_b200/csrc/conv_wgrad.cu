@@ -227,6 +227,20 @@ wgrad2_reduce_kernel(const float* __restrict__ partial, int splits, int taps, in
     }
 }
 
+// stem: dW[co][c][tap] = sum over slices of (partial[tap][co][c] + partial[tap][co][c + 8]) -- channels c and c + 8
+// of the 16-channel input are bf16(x) and its rounding residual, which share one weight (conv_stem.cu)
+__global__ void __launch_bounds__(256)
+stem_reduce_kernel(const float* __restrict__ partial, int splits, int Cin_true, float* __restrict__ dw) {
+    const int i = blockIdx.x * 256 + threadIdx.x;            // (tap, co, c < 8)
+    if (i >= 9 * 64 * 8) return;
+    const int c = i & 7, co = (i >> 3) & 63, tap = i >> 9;
+    if (c >= Cin_true) return;
+    const size_t total = (size_t)9 * 64 * 16, o = ((size_t)tap * 64 + co) * 16 + c;
+    float acc = 0.0f;
+    for (int s = 0; s < splits; ++s) acc += __ldg(partial + (size_t)s * total + o) + __ldg(partial + (size_t)s * total + o + 8);
+    dw[((size_t)co * Cin_true + c) * 9 + tap] = acc;
+}
+
 bool wgrad2_eligible(int Cin, int Cout, int ksize, int stride_h, int stride_w) {
     if (ksize != 3 || Cin % 64 != 0) return false;
     if (Cout % 128 == 0) return true;
@@ -417,9 +431,8 @@ int wgrad2_launch_stem(const CUtensorMap& map_x, const void* dz, float* dw, floa
     }
     conv_wgrad2_tc_kernel<<<p.n_tiles * p.splits, kWgThreads, smem, st>>>(map_dz, map_x, scratch, p);
     DELORA_CHECK_LAUNCH("conv_wgrad2_tc_kernel (stem)");
-    const size_t total4 = (size_t)9 * 64 * 16 / 4;
-    wgrad2_reduce_kernel<<<(unsigned)((total4 + 31) / 32), dim3(32, 8), 0, st>>>(scratch, p.splits, 9, 64, 16, Cin_true, dw);
-    DELORA_CHECK_LAUNCH("wgrad2_reduce_kernel");
+    stem_reduce_kernel<<<(9 * 64 * 8 + 255) / 256, 256, 0, st>>>(scratch, p.splits, Cin_true, dw);
+    DELORA_CHECK_LAUNCH("stem_reduce_kernel");
     return 0;
 }
 

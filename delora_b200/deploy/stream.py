@@ -40,7 +40,8 @@ class OdometryStream:
         self.relative = []                       # [1,4,4] numpy per frame pair, like Tester's lists
         self.use_cuda_graph = bool(use_cuda_graph)
         self.graph = None
-        self.model.config["use_tensor_core_encoder"] = True
+        # the model's own configuration decides the encoder path (tensor cores by default when eligible,
+        # models/model.py); the stream never edits the shared config dict
 
     # everything of a frame that runs on the device; static shapes and buffers (graph-capturable)
     def _frame(self):
@@ -54,8 +55,8 @@ class OdometryStream:
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)
+        saved = self.prev_image.clone()          # taken BEFORE the side stream is released: the warm-up frames write prev_image
         side.wait_stream(torch.cuda.current_stream())
-        saved = self.prev_image.clone()
         with torch.cuda.stream(side):
             for _ in range(3):                   # warm-up: allocator, tensor-map cache, cuBLAS handles
                 self._frame()

@@ -4,8 +4,8 @@ reference's keys (`epoch`, `model_state_dict`, `optimizer_state_dict`, `loss`, `
 :155-173).  MLflow / qqdm are used when importable and skipped otherwise.
 
 Data parallel: when launched under torchrun (WORLD_SIZE > 1) every rank trains on its own shard
-of the scan pairs and ALL parameter gradients (11.88 M) are averaged with one flat NCCL
-all-reduce per step; the loss kernels stay rank-local."""
+of the scan pairs and ALL parameter gradients (11.88 M) are averaged over NCCL, bucket by bucket and overlapped
+with the backward (parallel_grad.BucketedGradAllReduce); the loss kernels stay rank-local."""
 import os
 
 import numpy as np
@@ -13,7 +13,7 @@ import torch
 
 from . import deployer
 from ..data import batching
-from ..parallel_grad import FlatGradAllReduce
+from ..parallel_grad import make_grad_sync
 
 try:
     import mlflow
@@ -35,14 +35,15 @@ class Trainer(deployer.Deployer):
         if self.config["inference_only"]:
             print("Config error: Inference only does not make sense during training. Changing to inference_only=False.")
             self.config["inference_only"] = False
-        self.grad_sync = FlatGradAllReduce(self.model)    # no-op when WORLD_SIZE == 1
-        if self.grad_sync.world > 1:
-            inner_step = self.optimizer.step
+        # flat gradient buffer + per-bucket all-reduce overlapped with the backward (parallel_grad.py); a no-op
+        # wrapper on one process without the tensor-core encoder
+        self.grad_sync = make_grad_sync(self.model, self.config.get("grad_sync", "bucketed"))
+        inner_step = self.optimizer.step
 
-            def synced_step(*a, **k):
-                self.grad_sync.all_reduce()
-                return inner_step(*a, **k)
-            self.optimizer.step = synced_step
+        def synced_step(*a, **k):
+            self.grad_sync.finish()
+            return inner_step(*a, **k)
+        self.optimizer.step = synced_step
 
     @staticmethod
     def new_epoch_losses():
@@ -96,6 +97,11 @@ class Trainer(deployer.Deployer):
                       "loss_pl2pl_epoch", "visible_pixels_epoch"):
                 epoch_losses[k] = epoch_losses[k] / steps
             history.append(float(np.asarray(epoch_losses["loss_epoch"]).reshape(-1)[0]))
+            if self.grad_sync.world > 1:
+                # every rank must take the identity -> unsupervised switch in the same epoch: decide on the mean loss
+                t = torch.tensor([history[-1]], dtype=torch.float64, device=self.device)
+                torch.distributed.all_reduce(t)
+                history[-1] = float(t[0]) / self.grad_sync.world
             if self.grad_sync.rank == 0:
                 print("Epoch Summary: " + format(epoch, "05d") + ", loss: " + str(epoch_losses["loss_epoch"]) +
                       ", unsupervised: " + str(self.config["unsupervised_at_start"]))

@@ -57,12 +57,16 @@ class OdometryModel(torch.nn.Module):
 
     def _tensor_core_path(self):
         """The encoder trunk on the tcgen05 kernels (`models/tc_encoder.py`): bf16 NHWC activations,
-        forward and (autograd) backward — fprop, dgrad and wgrad all on the tensor cores.
-        Opt-in with config["use_tensor_core_encoder"] = True; needs the full-width model
-        (factor_fewer_resnet_channels == 1), no dropout and no pre-feature extractor."""
-        if not self.config.get("use_tensor_core_encoder", False):
+        forward and (autograd) backward -- fprop, dgrad and wgrad all on the tensor cores.
+        DEFAULT whenever the model is eligible: parameters on a CUDA device, the full-width model
+        (factor_fewer_resnet_channels == 1, i.e. channel counts that are multiples of 64), no dropout, no
+        pre-feature extractor.  config["use_tensor_core_encoder"] = False opts out (torch / cuDNN convolutions,
+        the reference's `nn.Conv2d` path)."""
+        if not self.config.get("use_tensor_core_encoder", True):
             return None
         if self.pre_feature_extraction or self.config["factor_fewer_resnet_channels"] != 1 or self.config["use_dropout"]:
+            return None
+        if not self.resnet.conv1.weight.is_cuda:
             return None
         if getattr(self, "_tc_encoder", None) is None:
             from . import tc_encoder

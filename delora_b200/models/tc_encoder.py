@@ -90,6 +90,15 @@ class TensorCoreEncoder:
         self._wtable = None
         self._buf = {}
         self._slots = []
+        # data-parallel hook (parallel_grad.BucketedGradAllReduce): weight gradients are written into these views
+        # (trunk_parameters() order) and every finished group is announced through grad_ready(list of indices)
+        self.grad_views = None
+        self.grad_ready = None
+        idx, self._block_param_idx = 1, []
+        for blk in self.blocks:
+            n = 3 if blk["has_wd"] else 2
+            self._block_param_idx.append(list(range(idx, idx + n)))
+            idx += n
 
     def _weight_buffers(self):
         params = self.trunk_parameters()
@@ -228,6 +237,23 @@ class TensorCoreEncoder:
                     params.append(blk.downsample[0].weight)
         return params
 
+    def trunk_parameter_groups(self):
+        """Trunk parameter indices grouped in the order the backward finishes them: layer4, layer3, the rest."""
+        nb = len(self.blocks)
+        per_layer = nb // 4 if nb % 4 == 0 and nb >= 4 else None
+        if per_layer is None:
+            return [[i for blk in reversed(self._block_param_idx) for i in blk] + [0]]
+        def blocks(lo, hi):
+            return [i for b in range(hi - 1, lo - 1, -1) for i in self._block_param_idx[b]]
+        return [blocks(3 * per_layer, nb), blocks(2 * per_layer, 3 * per_layer), blocks(0, 2 * per_layer) + [0]]
+
+    def _gout(self, index):
+        return self.grad_views[index] if self.grad_views is not None else None
+
+    def _announce(self, indices):
+        if self.grad_ready is not None:
+            self.grad_ready(indices)
+
     def pooled_features(self, image_1, image_2):
         """[B, C4] average-pooled encoder features with autograd through the tcgen05 kernels."""
         return _EncoderTrainFn.apply(self, image_1.float().contiguous(), image_2.float().contiguous(),
@@ -302,13 +328,16 @@ class TensorCoreEncoder:
             blk = blocks[i]
             (ch, cw), (oh, ow), (sh, sw) = blk["in_hw"], blk["out_hw"], blk["stride"]
             cin, cout = blk["x"].shape[3], blk["out"].shape[3]
-            g_w2 = ops.conv2d_wgrad(blk["t1"], dz2, oh, ow, 3, (1, 1))
+            pidx = self._block_param_idx[i]
+            g_w2 = ops.conv2d_wgrad(blk["t1"], dz2, oh, ow, 3, (1, 1), out=self._gout(pidx[1]))
             dz1 = ops.conv2d_fprop(dz2, blk["f2"], oh, ow, 3, (1, 1), act_bwd, None,
                                    self._buffer(f"g{i}a", b, oh, ow, cout, dev), saved=blk["t1"])
-            g_w1 = ops.conv2d_wgrad(blk["x"], dz1, ch, cw, 3, (sh, sw))
+            g_w1 = ops.conv2d_wgrad(blk["x"], dz1, ch, cw, 3, (sh, sw), out=self._gout(pidx[0]))
             g_wd = None
             if blk["wd"] is not None:
-                g_wd = ops.conv2d_wgrad(blk["x"], dz2, ch, cw, 1, (sh, sw))
+                g_wd = ops.conv2d_wgrad(blk["x"], dz2, ch, cw, 1, (sh, sw), out=self._gout(pidx[2]))
+            self._announce(pidx)       # this block's weight gradients are enqueued: its bucket may start reducing
+            if blk["wd"] is not None:
                 # 1x1 strided downsample: its data gradient is the 1x1 convolution of the SMALL dz, scattered to the
                 # strided positions afterwards (2-4x fewer MMAs than convolving the zero-upsampled gradient)
                 small = ops.conv2d_fprop(dz2, blk["fd"], oh, ow, 1, (1, 1), ops.ACT_NONE, None,
@@ -339,9 +368,10 @@ class TensorCoreEncoder:
                                                         w2, 64, act_id, dz0.data_ptr(), ops._stream()),
                        "delora_maxpool_w_bwd_nhwc_bf16")
         if st["stem_fast"]:
-            g_stem = ops.stem_wgrad(st["x_in"], dz0, h, w, st["w_stem"].shape[1])
+            g_stem = ops.stem_wgrad(st["x_in"], dz0, h, w, st["w_stem"].shape[1], out=self._gout(0))
         else:
-            g_stem = ops.conv2d_wgrad(st["x_in"], dz0, h, w, 3, (1, 2), cin_true=st["w_stem"].shape[1])
+            g_stem = ops.conv2d_wgrad(st["x_in"], dz0, h, w, 3, (1, 2), cin_true=st["w_stem"].shape[1], out=self._gout(0))
+        self._announce([0])
         grads = [g_stem]
         for g_w1, g_w2, g_wd in reversed(grads_rev):
             grads += [g_w1, g_w2]

@@ -321,8 +321,17 @@ def conv2d_dgrad(dz, w_flip, hin, win, stride, act=ACT_NONE, residual=None, out=
 _wgrad_scratch = {}
 
 
-def conv2d_wgrad(x, dz, hin, win, ksize, stride, cin_true=None):
-    """x [B,Hin+2,Win+2,Cin], dz [B,Hout+2,Wout+2,Cout] (bf16 padded NHWC) -> dW [Cout,Cin_true,k,k] fp32."""
+def _grad_out(out, shape, device):
+    if out is None:
+        return torch.empty(shape, dtype=torch.float32, device=device)
+    if tuple(out.shape) != tuple(shape) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError(f"gradient output must be a contiguous fp32 tensor of shape {tuple(shape)}")
+    return out
+
+
+def conv2d_wgrad(x, dz, hin, win, ksize, stride, cin_true=None, out=None):
+    """x [B,Hin+2,Win+2,Cin], dz [B,Hout+2,Wout+2,Cout] (bf16 padded NHWC) -> dW [Cout,Cin_true,k,k] fp32
+    (written into `out` when given: a contiguous fp32 tensor of that shape, e.g. a slice of a flat gradient buffer)."""
     b, _, _, cin = x.shape
     cout = dz.shape[3]
     cin_true = cin if cin_true is None else int(cin_true)
@@ -334,7 +343,7 @@ def conv2d_wgrad(x, dz, hin, win, ksize, stride, cin_true=None):
     if scratch is None:
         scratch = torch.empty((n,), dtype=torch.float32, device=x.device)
         _wgrad_scratch[key] = scratch
-    dw = torch.empty((cout, cin_true, ksize, ksize), dtype=torch.float32, device=x.device)
+    dw = _grad_out(out, (cout, cin_true, ksize, ksize), x.device)
     _lib.check(L.delora_conv2d_wgrad_bf16(_req(x, torch.bfloat16, "x"), _req(dz, torch.bfloat16, "dz"), dw.data_ptr(),
                                           scratch.data_ptr(), b, hin, win, cin, cin_true, cout, ksize, stride[0],
                                           stride[1], _stream()), "delora_conv2d_wgrad_bf16")
@@ -423,7 +432,7 @@ def stem_fprop(x16, w_stem, h, w, act, out=None):
     return out
 
 
-def stem_wgrad(x16, dz, h, w, cin_true):
+def stem_wgrad(x16, dz, h, w, cin_true, out=None):
     """-> dW [64, cin_true, 3, 3] fp32."""
     b = x16.shape[0]
     L = _lib.lib()
@@ -433,7 +442,7 @@ def stem_wgrad(x16, dz, h, w, cin_true):
     if scratch is None:
         scratch = torch.empty((n,), dtype=torch.float32, device=x16.device)
         _wgrad_scratch[key] = scratch
-    dw = torch.empty((64, cin_true, 3, 3), dtype=torch.float32, device=x16.device)
+    dw = _grad_out(out, (64, cin_true, 3, 3), x16.device)
     _lib.check(L.delora_stem_wgrad_bf16(_req(x16, torch.bfloat16, "x16"), _req(dz, torch.bfloat16, "dz"), dw.data_ptr(),
                                         scratch.data_ptr(), b, h, w, int(cin_true), _stream()), "delora_stem_wgrad_bf16")
     return dw

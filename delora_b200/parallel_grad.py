@@ -1,16 +1,28 @@
-"""Data-parallel gradient synchronisation: ONE flat all-reduce of every parameter gradient per
-step (11.88 M fp32 = 47.5 MB for the default model), NCCL over NVLink on GPUs, gloo in the CPU
-tests.  The scan-pair kernels are rank-local; this is the only collective of the training step
-(SURVEY.md §8(e)).  One process per GPU, launched with torchrun."""
+"""Data-parallel gradient synchronisation (the reference itself is single-process,
+`src/deploy/deployer.py:329-342` divides the summed loss by the batch size -- with equal per-rank batches the mean
+over ranks of the per-rank mean reproduces it).  The scan-pair kernels are rank-local; the gradient all-reduce is the
+only collective of the training step.  One process per GPU, launched with torchrun.
+
+`BucketedGradAllReduce` (the training path): every gradient is a view of ONE persistent flat fp32 buffer (11.88 M
+elements = 47.5 MB for the default model) laid out in BACKWARD order as a few buckets (heads + fc | layer4 | layer3 |
+layer2 + layer1 + stem).  The tensor-core encoder writes its weight gradients straight into the flat slices (no copies)
+and announces each group from inside its backward, so NCCL reduces layer4 (33.6 MB) on its own stream while the
+backward of layers 3 -> 1 still runs; only the last small bucket is exposed.  `FlatGradAllReduce` (one blocking
+all-reduce after backward) is kept for the CPU / gloo tests and as the measured baseline of the overlap."""
 
 import torch
 import torch.distributed as dist
 
 
+def _world(process_group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(process_group), dist.get_rank(process_group)
+    return 1, 0
+
+
 class FlatGradAllReduce:
     def __init__(self, module, process_group=None):
-        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
-        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self.world, self.rank = _world(process_group)
         self.group = process_group
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.numel = sum(p.numel() for p in self.params)
@@ -43,6 +55,142 @@ class FlatGradAllReduce:
                 p.grad = torch.empty_like(p)
             p.grad.copy_(self.flat[off:off + n].view_as(p))
             off += n
+
+    finish = all_reduce
+
+
+class BucketedGradAllReduce:
+    """Flat gradient buffer + bucketed, overlapped all-reduce.  Usage per step:
+        optimizer.zero_grad(set_to_none=True); loss.backward(); sync.finish(); optimizer.step()
+    `finish()` waits for the outstanding collectives (stream-ordered, no host sync) and makes every `p.grad` the
+    view of the flat buffer that holds the averaged gradient.  With WORLD_SIZE == 1 the buffer and the direct
+    gradient writes are still used (no copies), only the collectives are skipped."""
+
+    def __init__(self, module, encoder=None, process_group=None, enabled=True):
+        self.world, self.rank = _world(process_group)
+        self.group = process_group
+        self.enabled = bool(enabled)
+        params = [p for p in module.parameters() if p.requires_grad]
+        trunk = list(encoder.trunk_parameters()) if encoder is not None else []
+        trunk_ids = {id(p) for p in trunk}
+        others = [p for p in params if id(p) not in trunk_ids]
+        # buckets in the order their gradients become ready during backward
+        buckets = [others]
+        if trunk:
+            groups = encoder.trunk_parameter_groups()          # list of lists of trunk indices, backward order
+            for g in groups:
+                buckets.append([trunk[i] for i in g])
+            self._trunk_bucket = {}
+            for bi, g in enumerate(groups):
+                for i in g:
+                    self._trunk_bucket[i] = bi + 1
+        self.buckets = [b for b in buckets]
+        device = params[0].device
+        total = sum(p.numel() for p in params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.views, self.ranges, self._bucket_of = {}, [], {}
+        off = 0
+        for bi, b in enumerate(self.buckets):
+            start = off
+            for p in b:
+                n = p.numel()
+                self.views[id(p)] = self.flat[off:off + n].view_as(p)
+                self._bucket_of[id(p)] = bi
+                off += n
+            self.ranges.append((start, off))
+        self.params = params
+        self._pending = [0] * len(self.buckets)
+        self._works = []
+        self._launched = [False] * len(self.buckets)
+        if self.world > 1:
+            for p in params:
+                dist.broadcast(p.data, src=0, group=self.group)
+        # gradients produced by autograd itself (heads, fc, or everything when the tensor-core trunk is not used):
+        # copied into their flat slice as soon as they are accumulated
+        for p in params:
+            p.register_post_accumulate_grad_hook(self._on_autograd_grad)
+        self._trunk_params = trunk
+        self.encoder = encoder
+        if encoder is not None:
+            encoder.grad_views = [self.views[id(p)] for p in trunk]
+            encoder.grad_ready = self._on_trunk_grads
+        self._reset()
+
+    # ------------------------------------------------------------------ per-step state
+    def _reset(self):
+        self._pending = [len(b) for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+        self._ready = set()
+
+    def _mark(self, p):
+        if id(p) in self._ready:
+            return
+        self._ready.add(id(p))
+        bi = self._bucket_of[id(p)]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        if self._launched[bi]:
+            return
+        self._launched[bi] = True
+        if self.world == 1 or not self.enabled:
+            return
+        s, e = self.ranges[bi]
+        if e == s:
+            return
+        chunk = self.flat[s:e]
+        if dist.get_backend(self.group) == "nccl":
+            self._works.append((dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True), None))
+        else:
+            self._works.append((dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True), chunk))
+
+    def _on_autograd_grad(self, p):
+        if id(p) in self._ready:       # written in place by the encoder and possibly already being reduced: whatever
+            return                     # autograd stored in p.grad (the view itself or a copy of it) is replaced in finish()
+        view = self.views[id(p)]
+        if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+            view.copy_(p.grad)
+        self._mark(p)
+
+    def _on_trunk_grads(self, trunk_indices):
+        """Called by the encoder's backward right after the weight gradients of `trunk_indices` were enqueued
+        (written into `encoder.grad_views` on the current stream)."""
+        for i in trunk_indices:
+            self._mark(self._trunk_params[i])
+
+    def finish(self):
+        """Wait (stream-ordered) for the collectives and point every p.grad at its averaged flat view."""
+        for bi in range(len(self.buckets)):        # parameters that received no gradient this step count as zeros
+            if not self._launched[bi]:
+                for p in self.buckets[bi]:
+                    if p.grad is None:
+                        self.views[id(p)].zero_()
+                self._launch(bi)
+        for work, chunk in self._works:
+            work.wait()
+            if chunk is not None:
+                chunk.div_(self.world)
+        for p in self.params:
+            view = self.views[id(p)]
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                p.grad = view
+        self._reset()
+
+    all_reduce = finish
+
+
+def make_grad_sync(model, mode="bucketed", process_group=None):
+    """The gradient synchroniser of a training loop: "bucketed" (flat buffer, overlapped per-bucket all-reduce; also
+    used on one GPU with the tensor-core encoder, where it only removes gradient copies), "flat" (one blocking
+    all-reduce after backward), "none" (no collective: the measured reference for the exposed all-reduce time)."""
+    encoder = model._tensor_core_path() if hasattr(model, "_tensor_core_path") else None
+    world, _ = _world(process_group)
+    if mode == "flat" or (encoder is None and world == 1):
+        return FlatGradAllReduce(model, process_group)
+    return BucketedGradAllReduce(model, encoder=encoder, process_group=process_group, enabled=(mode != "none"))
 
 
 def shard_pairs(num_pairs, rank, world):

@@ -1,7 +1,7 @@
 """Full training step on synthetic scan pairs (BASELINE config #3 / #4 shape): projection of the raw
 scans -> normals -> tcgen05 encoder forward -> heads -> quaternion->T -> fused ICP losses with dL/dT ->
-backward through heads and the tcgen05 encoder (dgrad / wgrad) -> (flat NCCL gradient all-reduce when
-WORLD_SIZE > 1) -> Adam.  Used by bench.py (`train_step` key) and tests; mirrors Deployer.step
+backward through heads and the tcgen05 encoder (dgrad / wgrad), whose weight gradients land in one flat buffer and
+are all-reduced bucket by bucket over NCCL WHILE the backward still runs (WORLD_SIZE > 1, parallel_grad.py) -> Adam.  Used by bench.py (`train_step` key) and tests; mirrors Deployer.step
 (src/deploy/deployer.py:237-342) + Trainer's optimizer (src/deploy/trainer.py:23-24) with the normals
 computed in-line from the projected images (no preprocessed dataset on the bench box)."""
 import torch
@@ -10,11 +10,12 @@ from . import ops
 from .deploy.deployer import _FusedIcp
 from .models.model import OdometryModel
 from .models.model_parts import GeometryHandler
-from .parallel_grad import FlatGradAllReduce
+from .parallel_grad import make_grad_sync
 
 
 class SyntheticTrainStep:
-    def __init__(self, cfg, batch, n_max, dataset="kitti", use_tensor_cores=True, lr=1e-5, identity_init=True):
+    def __init__(self, cfg, batch, n_max, dataset="kitti", use_tensor_cores=True, lr=1e-5, identity_init=True,
+                 grad_sync="bucketed", autocast_bf16=False):
         self.cfg = dict(cfg)
         self.cfg.update({"pre_feature_extraction": False, "resnet_outputs": 1000, "use_dropout": False,
                          "layers": [2, 2, 2, 2], "factor_fewer_resnet_channels": 1, "activation_fct": "tanh",
@@ -34,8 +35,9 @@ class SyntheticTrainStep:
                                    (self.model.fully_connected_translation, [0.0, 0.0, 0.0])):
                     head[3].weight.zero_()
                     head[3].bias.copy_(torch.tensor(bias, device=self.device))
+        self.autocast_bf16 = bool(autocast_bf16)       # torch / cuDNN path only: the reference stack under bf16 autocast
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr)
-        self.sync = FlatGradAllReduce(self.model)
+        self.sync = make_grad_sync(self.model, grad_sync)
         self.scratch = ops.icp_scratch(self.B, self.H * self.W, self.device)
         self.points = torch.zeros((2 * self.B, 3, self.N), dtype=torch.float32, device=self.device)
         self.n_points = torch.zeros((2 * self.B,), dtype=torch.int32, device=self.device)
@@ -52,7 +54,9 @@ class SyntheticTrainStep:
                                             self.cfg["min_num_points_in_neighborhood_to_determine_point_class"],
                                             grids=True)
         self.optimizer.zero_grad(set_to_none=True)
-        translations, quaternions = self.model(image_1=image[:b].contiguous(), image_2=image[b:].contiguous())
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast_bf16):
+            translations, quaternions = self.model(image_1=image[:b].contiguous(), image_2=image[b:].contiguous())
+        translations, quaternions = translations.float(), quaternions.float()
         T = GeometryHandler.get_transformation_matrix_quaternion(translations, quaternions, self.device)
         total, parts = _FusedIcp.apply(T, pts_grid[b:].contiguous(), nrm_grid[b:].contiguous(),
                                        pts_grid[:b].contiguous(), nrm_grid[:b].contiguous(),
@@ -60,6 +64,6 @@ class SyntheticTrainStep:
                                        ops.LOSS_PO2PL | ops.LOSS_PL2PL, self.scratch)
         loss = total.mean()
         loss.backward()
-        self.sync.all_reduce()
+        self.sync.finish()
         self.optimizer.step()
         return loss.detach(), parts

@@ -138,7 +138,7 @@ def check_stem(b, h, w, time_it=True):
     wst = torch.empty((3, 64, 64), dtype=torch.bfloat16, device=DEV)
     ops.stem_weight_prep(wt, wst)
     y = ops.stem_fprop(x16, wst, h, w, ops.ACT_TANH)
-    x = torch.cat([img1, img2], 1).to(torch.bfloat16).float()
+    x = torch.cat([img1, img2], 1)                 # the stem carries bf16(x) + bf16(x - bf16(x)): ~fp32 input precision
     ref = torch.tanh(F.conv2d(F.pad(x, (1, 1, 0, 0), mode="circular"), wt.to(torch.bfloat16).float(), stride=(1, 2), padding=(1, 0)))
     got = ops.nhwc_to_nchw(y, h, w // 2)
     e1 = (got - ref).abs().max().item()

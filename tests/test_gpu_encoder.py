@@ -78,6 +78,7 @@ def test_tensor_core_encoder_matches_torch_model(h, w, cuda_lib):
     cfg.update({"pre_feature_extraction": False, "resnet_outputs": 1000, "use_dropout": False, "layers": [2, 2, 2, 2],
                 "factor_fewer_resnet_channels": 1, "activation_fct": "tanh", "use_single_mlp_at_output": False})
     torch.manual_seed(0)
+    cfg["use_tensor_core_encoder"] = False                 # the fp32 torch / cuDNN path is the reference here
     model = OdometryModel(cfg).to(DEV).eval()
     enc = TensorCoreEncoder(model)
     g = torch.Generator(device=DEV).manual_seed(1)

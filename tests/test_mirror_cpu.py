@@ -135,6 +135,105 @@ def test_gradient_allreduce_world_size_2_gloo(tmp_path):
     assert torch.allclose(r0["grad"], ref, rtol=1e-5, atol=1e-6)
 
 
+class _FakeTrunk:
+    """Stands in for the tensor-core encoder on the CPU: two 'trunk' weights whose gradients are written straight
+    into the flat views and announced group by group from inside backward (parallel_grad's encoder protocol)."""
+
+    def __init__(self):
+        self.w = [torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(3, 3))]
+        self.grad_views, self.grad_ready = None, None
+
+    def trunk_parameters(self):
+        return self.w
+
+    def trunk_parameter_groups(self):
+        return [[1], [0]]                                   # backward finishes w[1] first
+
+    def apply(self, x):
+        enc = self
+
+        class Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x, w0, w1):
+                h = torch.tanh(x @ w0.t())
+                ctx.save_for_backward(x, w0, w1, h)
+                return h @ w1.t()
+
+            @staticmethod
+            def backward(ctx, g):
+                x, w0, w1, h = ctx.saved_tensors
+                g1 = g.t() @ h
+                out1 = enc.grad_views[1] if enc.grad_views is not None else torch.empty_like(w1)
+                out1.copy_(g1)
+                if enc.grad_ready is not None:
+                    enc.grad_ready([1])
+                gh = (g @ w1) * (1 - h * h)
+                out0 = enc.grad_views[0] if enc.grad_views is not None else torch.empty_like(w0)
+                out0.copy_(gh.t() @ x)
+                if enc.grad_ready is not None:
+                    enc.grad_ready([0])
+                return None, out0, out1
+        return Fn.apply(x, self.w[0], self.w[1])
+
+
+class _FakeModel(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.trunk = _FakeTrunk()
+        self.w0, self.w1 = self.trunk.w
+        self.head = torch.nn.Linear(3, 2)
+
+    def forward(self, x):
+        return self.head(self.trunk.apply(x))
+
+
+def _bucket_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from delora_b200.parallel_grad import BucketedGradAllReduce, shard_pairs
+    torch.manual_seed(200 + rank)
+    model = _FakeModel()
+    sync = BucketedGradAllReduce(model, encoder=model.trunk)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    x = torch.arange(8 * 5, dtype=torch.float32).view(8, 5) / 10.0
+    shard = shard_pairs(8, rank, world)
+    grads = []
+    for _ in range(2):                                     # two steps: the per-step bucket state must re-arm
+        opt.zero_grad(set_to_none=True)
+        model(x[shard]).pow(2).sum().backward()
+        sync.finish()
+        assert all(p.grad.data_ptr() == sync.views[id(p)].data_ptr() for p in model.parameters())
+        grads.append(torch.cat([p.grad.reshape(-1).clone() for p in model.parameters()]))
+        opt.step()
+    torch.save({"grads": grads, "w": torch.cat([p.data.reshape(-1) for p in model.parameters()])},
+               os.path.join(out, f"b{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_bucketed_overlapped_allreduce_world_size_2_gloo(tmp_path):
+    """BucketedGradAllReduce (flat gradient buffer, per-bucket all-reduce launched from inside backward): two gloo
+    ranks end up with the gradient of the half-summed full batch, for two consecutive steps, and stay in lock step."""
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_bucket_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "b0.pt"), torch.load(tmp_path / "b1.pt")
+    assert torch.equal(r0["w"], r1["w"])
+    for g0, g1 in zip(r0["grads"], r1["grads"]):
+        assert torch.equal(g0, g1)
+    torch.manual_seed(200)
+    model = _FakeModel()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    x = torch.arange(8 * 5, dtype=torch.float32).view(8, 5) / 10.0
+    for step in range(2):
+        opt.zero_grad(set_to_none=True)
+        (model(x).pow(2).sum() / 2).backward()
+        ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        assert torch.allclose(r0["grads"][step], ref, rtol=1e-5, atol=1e-6), step
+        opt.step()
+
+
 def test_kitti_bin_reader(tmp_path):
     """`data.kitti_scans.KITTIPointCloudDataset`: sorted *.bin files -> [4, N] float32 (src/data/kitti_scans.py:35-50)."""
     from delora_b200 import synthetic
