@@ -53,6 +53,8 @@ struct RowsParams {
     int act;
     int w_stages;
     int a_stage_bytes;
+    int n_tile;                                    // pixel-on-M mode: output channels per job (MMA N) = Cout <= 128
+    int w_tile_bytes;                              // bytes of one filter tile in the ring
     int res_grid;                                  // 1: `residual` is given on the job grid [B, Hg+2, Wg+2, Cout] and belongs
                                                    //    to phase (0, 0) only (data gradient of a 1x1 strided downsample)
     RowsPhase phase[kRowsMaxPhases];
@@ -78,7 +80,11 @@ __device__ __forceinline__ RowsJob rows_decode(const RowsParams& p, int job, int
 //         tile of its own R rows): per SM the MMA reads 64 instead of 128 B/clk of shared memory and each filter
 //         byte is fetched for twice the pixels -- measured necessary: the shared-memory port (128 B/clk, MMA operand
 //         reads + TMA fills) is what bounds these kernels (scripts/umma_probe2.cu, profiles/r02_umma_probe2.log).
-template <int CG>
+// PIXM (layers with Cout = 64 / 128, where M = 128 output channels cannot be filled): the roles are swapped back --
+//         M = the 128 PIXELS of a row segment (A operand = halo-tile rows, same shifted descriptors), N = all Cout output
+//         channels (B operand = filter tile [Cout / CG][64]); a thread of the epilogue owns a pixel, no transpose.
+//         With CG = 2 the pair covers 2 x 128 pixels and each CTA loads half of the filter rows.
+template <int CG, bool PIXM>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __nv_bfloat16* __restrict__ residual, const __nv_bfloat16* __restrict__ saved,
@@ -87,7 +93,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint8_t* smem = DELORA_ALIGNED_SMEM(smem_raw);
     uint8_t* smem_a = smem;                                        // 2 halo-tile stages
     uint8_t* smem_w = smem_a + 2 * p.a_stage_bytes;                // filter ring
-    float* stage = reinterpret_cast<float*>(smem_w + p.w_stages * kWTileBytes);   // 4 x 4 KB transpose buffers
+    float* stage = reinterpret_cast<float*>(smem_w + p.w_stages * p.w_tile_bytes);   // 4 x 4 KB transpose buffers
     uint64_t* a_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage) + 4 * 4096);
     uint64_t* a_empty = a_full + 2;
     uint64_t* acc_full = a_empty + 2;
@@ -148,17 +154,18 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             for (int job = unit; job < p.n_jobs; job += n_units) {
                 const RowsJob j = rows_decode(p, job, CG);
                 const RowsPhase& ph = p.phase[j.ph];
-                const int co0 = (j.ct * CG + (int)rank) * 128;
+                const int co0 = PIXM ? j.ct * p.n_tile + (int)rank * (p.n_tile / CG) : (j.ct * CG + (int)rank) * 128;
+                const uint32_t wb = (uint32_t)p.w_tile_bytes;
                 for (int kc = 0; kc < p.kchunks; ++kc)
                     for (int t = 0; t < ph.ntaps; ++t, ++it) {
                         const uint32_t s = it % S;
                         mbar_wait(w_empty + s, ((it / S) & 1) ^ 1);
                         if (CG == 2) {
-                            if (rank == 0) mbar_expect_tx(w_full + s, 2 * kWTileBytes);
-                            tma_load_2d_2sm(smem_w + s * kWTileBytes, &map_w, w_full + s, (int)ph.wtap[t] * p.Cin + kc * 64, co0);
+                            if (rank == 0) mbar_expect_tx(w_full + s, 2 * wb);
+                            tma_load_2d_2sm(smem_w + s * wb, &map_w, w_full + s, (int)ph.wtap[t] * p.Cin + kc * 64, co0);
                         } else {
-                            mbar_expect_tx(w_full + s, kWTileBytes);
-                            tma_load_2d(smem_w + s * kWTileBytes, &map_w, w_full + s, (int)ph.wtap[t] * p.Cin + kc * 64, co0);
+                            mbar_expect_tx(w_full + s, wb);
+                            tma_load_2d(smem_w + s * wb, &map_w, w_full + s, (int)ph.wtap[t] * p.Cin + kc * 64, co0);
                         }
                     }
             }
@@ -169,7 +176,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         // register -> uniform-register broadcasts); one elected lane issues the tcgen05 instructions.
         if (rank == 0) {
             const bool issuer = elect_one();
-            const int N = CG * p.NS, R = p.R, kchunks = p.kchunks;
+            const int N = PIXM ? p.n_tile : CG * p.NS, R = p.R, kchunks = p.kchunks;
             const uint32_t idesc = make_idesc(128 * CG, N, 0, 0);
             const uint64_t desc_hi = make_smem_desc(0);          // everything but the start-address field
             const uint32_t row_step = (uint32_t)(pitch * 128) >> 4;             // next tile row, in 16-byte units
@@ -201,19 +208,18 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                             mbar_wait(w_full + ws, wph);
                             tc_fence_after();
                             if (issuer) {
-                                const uint64_t dw = desc_hi | (uint64_t)(w_lo0 + ws * (kWTileBytes >> 4));
+                                const uint64_t dw = desc_hi | (uint64_t)(w_lo0 + ws * ((uint32_t)p.w_tile_bytes >> 4));
                                 const uint32_t x_lo = a_lo + xoff[t];
                                 const uint32_t first = (kc == 0 && t == 0) ? 0u : 1u;
                                 for (int i = 0; i < R; ++i) {
                                     const uint64_t dx = desc_hi | (uint64_t)(x_lo + (uint32_t)i * row_step);
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {   // 64 channels = 4 x K16; +32 bytes = +2 in 16-byte units
+                                        const uint64_t da = (PIXM ? dx : dw) + (uint64_t)(k * 2), db = (PIXM ? dw : dx) + (uint64_t)(k * 2);
                                         if (CG == 2)
-                                            tcgen05_mma_bf16_2sm(acc + (uint32_t)(i * N), dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2),
-                                                                 idesc, (k > 0) ? 1u : first);
+                                            tcgen05_mma_bf16_2sm(acc + (uint32_t)(i * N), da, db, idesc, (k > 0) ? 1u : first);
                                         else
-                                            tcgen05_mma_bf16(acc + (uint32_t)(i * N), dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2),
-                                                             idesc, (k > 0) ? 1u : first);
+                                            tcgen05_mma_bf16(acc + (uint32_t)(i * N), da, db, idesc, (k > 0) ? 1u : first);
                                     }
                                 }
                                 if (CG == 2) tcgen05_commit_2sm(w_empty + ws); else tcgen05_commit(w_empty + ws);
@@ -246,6 +252,38 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const uint32_t ab = j_it & 1;
             mbar_wait(acc_full + ab, (j_it >> 1) & 1);
             tc_fence_after();
+            if (PIXM) {
+                // lane = pixel of the segment, columns = output channels: no transpose
+                const int wl = quarter * 32 + lane, wg = j.w0 + wl;
+                const int wo = wg * p.out_sw + ph.ow;
+                for (int i = 0; i < p.R; ++i) {
+                    const int hg = j.h0 + (int)rank * p.R + i;
+                    const int ho = hg * p.out_sh + ph.oh;
+                    const bool in_range = hg < p.Hg && wg < p.Wg && ho < p.Hout && wo < p.Wout;
+                    const bool use_res = residual != nullptr && (!p.res_grid || (ph.oh | ph.ow) == 0);
+                    for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                        const int c_first = j.ct * p.n_tile + c0;
+                        const size_t off = (((size_t)j.b * Hp + (ho + 1)) * Wp + (wo + 1)) * p.Cout + c_first;
+                        const size_t roff = p.res_grid
+                            ? (((size_t)j.b * (p.Hg + 2) + (hg + 1)) * (p.Wg + 2) + (wg + 1)) * p.Cout + c_first : off;
+                        EpiloguePrefetch pf;
+                        if (in_range)
+                            epilogue_prefetch32(pf, use_res ? residual + roff : nullptr, saved + (p.act >= 3 ? off : 0), 0, p.act);
+                        uint32_t acc[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * 256 + (uint32_t)(i * p.n_tile + c0), acc);
+                        if (in_range) {
+                            float v[32];
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]);
+                            epilogue_finish32(v, pf, use_res, y, off, p.act, wo == 0, wo == p.Wout - 1, (size_t)p.Wout * p.Cout);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (CG == 2) mbar_arrive_leader(acc_empty + ab); else mbar_arrive(acc_empty + ab); }
+                continue;
+            }
             const int c_first = (j.ct * CG + (int)rank) * 128 + quarter * 32;
             for (int cb = 0; cb < n_blocks; ++cb) {
                 // this thread's pixel of the block; its residual / saved loads go out before the TMEM read
@@ -290,7 +328,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
 // ---------------------------------------------------------------- host side
 static int rows_encode_maps(CUtensorMap* mx, CUtensorMap* mw, const void* x, const void* w, int B, int Hin, int Win,
-                            int Cin, int Cout, int wtaps, int NS, int R) {
+                            int Cin, int Cout, int wtaps, int NS, int R, int w_rows) {
     PFN_cuTensorMapEncodeTiled_v12000 encode = get_tensor_map_encoder();
     if (!encode) return 1;
     const int Hp = Hin + 2, Wp = Win + 2;
@@ -307,7 +345,7 @@ static int rows_encode_maps(CUtensorMap* mx, CUtensorMap* mw, const void* x, con
     {
         cuuint64_t dims[2] = {(cuuint64_t)wtaps * Cin, (cuuint64_t)Cout};
         cuuint64_t strides[1] = {(cuuint64_t)wtaps * Cin * 2};
-        cuuint32_t box[2] = {64, 128};
+        cuuint32_t box[2] = {64, (cuuint32_t)w_rows};
         cuuint32_t estr[2] = {1, 1};
         if (encode(mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -319,7 +357,7 @@ static int rows_encode_maps(CUtensorMap* mx, CUtensorMap* mw, const void* x, con
 
 // Tensor maps depend only on (pointers, shapes); the encoder's activations, filters and gradients live in
 // persistent buffers, so a small per-thread cache removes the encode cost from the 40 launches of a step.
-struct RowsMapKey { const void* x; const void* w; int B, Hin, Win, Cin, Cout, wtaps, NS, R; };
+struct RowsMapKey { const void* x; const void* w; int B, Hin, Win, Cin, Cout, wtaps, NS, R, w_rows; };
 struct RowsMapEntry { RowsMapKey k; CUtensorMap mx, mw; };
 
 static const RowsMapEntry* rows_get_maps(const RowsMapKey& key) {
@@ -328,12 +366,12 @@ static const RowsMapEntry* rows_get_maps(const RowsMapKey& key) {
     for (int i = 0; i < used; ++i) {
         const RowsMapKey& c = cache[i].k;
         if (c.x == key.x && c.w == key.w && c.B == key.B && c.Hin == key.Hin && c.Win == key.Win && c.Cin == key.Cin &&
-            c.Cout == key.Cout && c.wtaps == key.wtaps && c.NS == key.NS && c.R == key.R)
+            c.Cout == key.Cout && c.wtaps == key.wtaps && c.NS == key.NS && c.R == key.R && c.w_rows == key.w_rows)
             return &cache[i];
     }
     RowsMapEntry& e = cache[next];
     if (rows_encode_maps(&e.mx, &e.mw, key.x, key.w, key.B, key.Hin, key.Win, key.Cin, key.Cout, key.wtaps, key.NS,
-                         key.R) != 0)
+                         key.R, key.w_rows) != 0)
         return nullptr;
     e.k = key;
     const RowsMapEntry* out = &e;
@@ -370,8 +408,13 @@ bool rows_use_pairs() {
 }
 void rows_set_pairs(int on) { g_rows_pairs = on ? 1 : 0; }
 
-bool conv_rows_eligible(int Cin, int Cout, int ksize) {
-    return Cin % 64 == 0 && Cout % 128 == 0 && (ksize == 3 || ksize == 1);
+// pixel-on-M mode: Cout = 64 or 128 and a job grid at least one full 128-pixel segment wide
+static bool rows_pixm(int Cout, int Wg) { return (Cout == 64 || Cout == 128) && Wg >= 128 && rows_use_pairs(); }
+
+// Wg = width of the job grid (the output width for a stride-1 convolution, ceil(Wout / stride_w) for a data gradient)
+bool conv_rows_eligible(int Cin, int Cout, int ksize, int Wg) {
+    if (Cin % 64 != 0 || !(ksize == 3 || ksize == 1)) return false;
+    return Cout % 128 == 0 || rows_pixm(Cout, Wg);
 }
 
 // stride-1 convolution (up_h = up_w = 1) or data gradient of a stride-(up_h, up_w) 3x3 convolution (x = output
@@ -420,30 +463,43 @@ int conv_rows_launch(const void* x, const void* w, const void* residual, const v
                 }
         p.n_phases = np;
     }
-    const int cg = (Cout % 256 == 0 && rows_use_pairs()) ? 2 : 1;
-    rows_pick_tile(p.Hg, p.Wg, cg, &p.NS, &p.R);
+    const bool pixm = rows_pixm(Cout, p.Wg);
+    const int cg = pixm ? (Cout == 128 ? 2 : 1) : ((Cout % 256 == 0 && rows_use_pairs()) ? 2 : 1);
+    if (pixm) {
+        p.NS = 128; p.R = (2 * cg <= p.Hg || cg == 1) ? 2 : 1;         // 128 pixels on M, R accumulators of Cout columns
+        if (p.R > p.Hg) p.R = p.Hg;
+        p.n_tile = Cout; p.w_tile_bytes = (Cout / cg) * 128;
+        p.co_tiles = 1;
+    } else {
+        rows_pick_tile(p.Hg, p.Wg, cg, &p.NS, &p.R);
+        p.n_tile = 0; p.w_tile_bytes = kWTileBytes;
+        p.co_tiles = Cout / (128 * cg);
+    }
     p.segs_w = (p.Wg + p.NS - 1) / p.NS;
     p.blocks_h = (p.Hg + p.R * cg - 1) / (p.R * cg);
-    p.co_tiles = Cout / (128 * cg);
     p.kchunks = Cin / 64;
     p.n_jobs = p.n_phases * B * p.blocks_h * p.segs_w * p.co_tiles;
     p.a_stage_bytes = (((p.NS + 2) * (p.R + 2) * 128) + 1023) / 1024 * 1024;
     const int fixed = 2 * p.a_stage_bytes + 4 * 4096 + 256 + 1024;
-    int ws = (227 * 1024 - fixed) / kWTileBytes;
+    int ws = (227 * 1024 - fixed) / p.w_tile_bytes;
     if (ws > 8) ws = 8;
     DELORA_CHECK_ARG(ws >= 2, "conv_rows: tile %dx%d leaves no room for the filter ring", p.NS, p.R);
     p.w_stages = ws;
-    const RowsMapKey key = {x, w, B, Hin, Win, Cin, Cout, ksize * ksize, p.NS, p.R};
+    const RowsMapKey key = {x, w, B, Hin, Win, Cin, Cout, ksize * ksize, p.NS, p.R, p.w_tile_bytes / 128};
     const RowsMapEntry* maps = rows_get_maps(key);
     DELORA_CHECK_ARG(maps != nullptr, "conv_rows: cuTensorMapEncodeTiled failed or is unavailable");
-    const size_t smem = (size_t)fixed + (size_t)ws * kWTileBytes;
+    const size_t smem = (size_t)fixed + (size_t)ws * p.w_tile_bytes;
     int dev = 0;
     cudaGetDevice(&dev);
     static bool attr_set[64] = {};
     if (dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_rows_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_rows_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_rows_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            e = cudaFuncSetAttribute(conv_rows_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_rows_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_rows_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         DELORA_CHECK_ARG(e == cudaSuccess, "conv_rows: shared-memory opt-in failed: %s", cudaGetErrorString(e));
         attr_set[dev] = true;
     }
@@ -458,8 +514,13 @@ int conv_rows_launch(const void* x, const void* w, const void* residual, const v
     const __nv_bfloat16* res_p = (const __nv_bfloat16*)residual;
     const __nv_bfloat16* sav_p = (const __nv_bfloat16*)saved;
     __nv_bfloat16* y_p = (__nv_bfloat16*)y;
-    cudaError_t le = (cg == 2) ? cudaLaunchKernelEx(&cfg, conv_rows_tc_kernel<2>, maps->mx, maps->mw, res_p, sav_p, y_p, p)
-                               : cudaLaunchKernelEx(&cfg, conv_rows_tc_kernel<1>, maps->mx, maps->mw, res_p, sav_p, y_p, p);
+    cudaError_t le;
+    if (pixm)
+        le = (cg == 2) ? cudaLaunchKernelEx(&cfg, conv_rows_tc_kernel<2, true>, maps->mx, maps->mw, res_p, sav_p, y_p, p)
+                       : cudaLaunchKernelEx(&cfg, conv_rows_tc_kernel<1, true>, maps->mx, maps->mw, res_p, sav_p, y_p, p);
+    else
+        le = (cg == 2) ? cudaLaunchKernelEx(&cfg, conv_rows_tc_kernel<2, false>, maps->mx, maps->mw, res_p, sav_p, y_p, p)
+                       : cudaLaunchKernelEx(&cfg, conv_rows_tc_kernel<1, false>, maps->mx, maps->mw, res_p, sav_p, y_p, p);
     DELORA_CHECK_ARG(le == cudaSuccess, "conv_rows: launch failed: %s", cudaGetErrorString(le));
     DELORA_CHECK_LAUNCH("conv_rows_tc_kernel");
     return 0;
@@ -478,8 +539,9 @@ extern "C" int delora_conv2d_dgrad_bf16(const void* dz, const void* w_flip, cons
     DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin >= 1 && Win >= 1,
                      "delora_conv2d_dgrad_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
     DELORA_CHECK_ARG(stride_w == 1 || Win % 2 == 0, "delora_conv2d_dgrad_bf16: stride_w = 2 needs an even Win (got %d)", Win);
-    DELORA_CHECK_ARG(conv_rows_eligible(Cout, Cin, 3),
-                     "delora_conv2d_dgrad_bf16: needs Cin %% 128 == 0 and Cout %% 64 == 0 (got Cin=%d, Cout=%d)", Cin, Cout);
+    DELORA_CHECK_ARG(conv_rows_eligible(Cout, Cin, 3, (Win + stride_w - 1) / stride_w),
+                     "delora_conv2d_dgrad_bf16: needs Cout %% 64 == 0 and Cin %% 128 == 0 (or Cin = 64 / 128 with at least "
+                     "128 columns per phase); got Cin=%d, Cout=%d, Win=%d", Cin, Cout, Win);
     return conv_rows_launch(dz, w_flip, residual, saved, dx, B, Hin, Win, Cout, Cin, 3, stride_h, stride_w, act,
                             (cudaStream_t)stream, residual_strided);
 }

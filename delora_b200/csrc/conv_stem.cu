@@ -257,7 +257,7 @@ extern "C" int delora_stem_weight_prep_bf16(const float* w, int Cin, void* w_ste
 
 extern "C" int delora_conv_weight_prep_multi(const void* table, int n_layers, void* stream) {
     DELORA_CHECK_ARG(table && n_layers >= 1 && n_layers <= 65535, "delora_conv_weight_prep_multi: bad argument");
-    weight_prep_multi_kernel<<<dim3(64, (unsigned)n_layers), 256, 0, (cudaStream_t)stream>>>((const long long*)table);
+    weight_prep_multi_kernel<<<dim3(592, (unsigned)n_layers), 256, 0, (cudaStream_t)stream>>>((const long long*)table);
     DELORA_CHECK_LAUNCH("weight_prep_multi_kernel");
     return 0;
 }

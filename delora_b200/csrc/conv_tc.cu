@@ -717,7 +717,7 @@ static const TensorMaps* get_maps(const void* x, const void* w, int B, int Hin, 
 }  // namespace delora
 
 namespace delora {
-bool conv_rows_eligible(int Cin, int Cout, int ksize);
+bool conv_rows_eligible(int Cin, int Cout, int ksize, int Wg);
 void rows_set_pairs(int on);
 bool wgrad2_eligible(int Cin, int Cout, int ksize, int stride_h, int stride_w);
 int64_t wgrad2_scratch_floats(int B, int Hout, int Wout, int Cin, int Cout, int sw);
@@ -753,7 +753,7 @@ extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void
                      Cin, Cout);
     DELORA_CHECK_ARG((stride_h == 1 || stride_h == 2) && (stride_w == 1 || stride_w == 2) && Hin >= 1 && Win >= 1,
                      "delora_conv2d_fprop_bf16: stride (%d,%d) unsupported", stride_h, stride_w);
-    if (stride_h == 1 && stride_w == 1 && conv_rows_eligible(Cin, Cout, ksize) && use_conv_rows())
+    if (stride_h == 1 && stride_w == 1 && conv_rows_eligible(Cin, Cout, ksize, Win) && use_conv_rows())
         return conv_rows_launch(x, w, residual, saved, y, B, Hin, Win, Cin, Cout, ksize, 1, 1, act, (cudaStream_t)stream, 0);
     ConvParams p;
     p.B = B; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;

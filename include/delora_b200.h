@@ -256,7 +256,7 @@ int delora_conv_select_kernel(int rows_kernel);
  * residual_strided = 1: `residual` is [B,Hout+2,Wout+2,Cin] instead and is added at the input pixels
  * (stride_h * h, stride_w * w) only -- the data gradient of the block's 1x1 strided downsample (:134), which never
  * reaches the other pixels (replaces a zero-upsampled copy of it).
- * Needs Cin % 128 == 0, Cout % 64 == 0 and, for stride_w = 2, an even Win (an odd circular width mixes the phases at
+ * Needs Cout % 64 == 0, Cin % 128 == 0 (or Cin = 64 with >= 128 columns per phase) and, for stride_w = 2, an even Win (an odd circular width mixes the phases at
  * the seam: use delora_zero_upsample_nhwc_bf16 + delora_conv2d_fprop_bf16 there). */
 int delora_conv2d_dgrad_bf16(const void* dz, const void* w_flip, const void* residual, const void* saved, void* dx,
                              int B, int Hin, int Win, int Cin, int Cout, int stride_h, int stride_w, int act,

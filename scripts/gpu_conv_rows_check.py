@@ -91,7 +91,7 @@ def check_dgrad(b, cin, cout, h, w, stride, act, use_res, time_it=True):
         out = ops.padded_nhwc_zeros(b, h, w, cin, DEV)
         t_old = timed(lambda: old(out))
         L.delora_conv_select_kernel(2)
-        t_one = timed(lambda: ops.conv2d_dgrad(dz, wf, h, w, stride, act, res, out, saved))
+        t_one = timed(lambda: ops.conv2d_dgrad(dz, wf, h, w, stride, act, res, out, saved)) if cin % 128 == 0 else float("nan")
         L.delora_conv_select_kernel(1)
         t_new = timed(lambda: ops.conv2d_dgrad(dz, wf, h, w, stride, act, res, out, saved))
         fl = 2.0 * b * ho * wo * cout * cin * 9
@@ -194,12 +194,21 @@ def main():
     ok &= check_wgrad(1, 256, 512, 64, 45, (2, 2), False)
     ok &= check_wgrad(2, 512, 512, 32, 23, (1, 1), False)
     ok &= check_wgrad(1, 128, 256, 64, 90, (1, 2), False)
+    ok &= check_fprop(1, 64, 64, 8, 128, 3, 2, True, False)
+    ok &= check_fprop(2, 64, 64, 5, 200, 3, 1, True, False)
+    ok &= check_fprop(1, 128, 128, 3, 130, 3, 3, True, False)
+    ok &= check_fprop(1, 128, 64, 7, 256, 3, 4, False, False)
+    ok &= check_dgrad(1, 64, 128, 6, 512, (1, 2), 3, True, False)
+    ok &= check_dgrad(2, 128, 64, 9, 256, (1, 1), 0, False, False)
     ok &= check_stem(1, 8, 256, False)
     ok &= check_stem(2, 16, 180, False)
     ok &= check_stem(1, 64, 720, False)
     print(f"-- small cases done in {time.time() - t0:.1f} s, ok={ok}", flush=True)
     if not quick:
         # bench shapes (B = 16, 64x2048 image): L2 128ch @64x256, L3 256ch @64x128, L4 512ch @32x64
+        check_fprop(16, 64, 64, 64, 512, 3, 2, True)
+        check_fprop(16, 64, 64, 64, 512, 3, 3, True)
+        check_dgrad(16, 64, 128, 64, 512, (1, 2), 3, True)
         check_fprop(16, 128, 128, 64, 256, 3, 2, True)
         check_fprop(16, 256, 256, 64, 128, 3, 2, True)
         check_fprop(16, 512, 512, 32, 64, 3, 2, True)
