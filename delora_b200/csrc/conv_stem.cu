@@ -17,6 +17,7 @@
 //           persistent CTAs, 4 TMEM accumulators (epilogue overlaps the next tiles).
 //   wgrad:  the plan-driven kernel of conv_wgrad.cu (mode 2) on the same tensor map.
 #include <string.h>
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace delora {
@@ -27,6 +28,8 @@ constexpr int kStemTile = 128 * 128;            // one filter row of a tile: 128
 
 struct StemParams {
     int B, H, Wout, segs, n_jobs, act;
+    int out_f16;        // 1: store fp16 instead of bf16 (training: the pre-activation feeds only the two pool kernels,
+                        //    3 more mantissa bits keep the pool's argmax on the fp32 winner in near-ties)
 };
 
 __global__ void __launch_bounds__(kStemThreads, 1)
@@ -123,7 +126,32 @@ stem_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                    epilogue_finish32(v, pf, false, y, pix * 64 + c0, p.act, wo == 0, wo == p.Wout - 1, (size_t)p.Wout * 64);
+                    if (p.out_f16) {
+                        uint4 out[4];
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            __half2 hh[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                hh[e] = __floats2half2_rn(apply_act(v[j4 * 8 + e * 2], p.act), apply_act(v[j4 * 8 + e * 2 + 1], p.act));
+                            out[j4] = *reinterpret_cast<uint4*>(hh);
+                        }
+                        uint4* yp = reinterpret_cast<uint4*>(y + pix * 64 + c0);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) yp[j4] = out[j4];
+                        if (wo == 0) {
+                            uint4* hp = reinterpret_cast<uint4*>(y + (pix + p.Wout) * 64 + c0);
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) hp[j4] = out[j4];
+                        }
+                        if (wo == p.Wout - 1) {
+                            uint4* hp = reinterpret_cast<uint4*>(y + (pix - p.Wout) * 64 + c0);
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) hp[j4] = out[j4];
+                        }
+                    } else {
+                        epilogue_finish32(v, pf, false, y, pix * 64 + c0, p.act, wo == 0, wo == p.Wout - 1, (size_t)p.Wout * 64);
+                    }
                 }
             }
             tc_fence_before();
@@ -263,12 +291,13 @@ extern "C" int delora_conv_weight_prep_multi(const void* table, int n_layers, vo
 }
 
 extern "C" int delora_stem_fprop_bf16(const void* x16, const void* w_stem, void* y, int B, int H, int W, int act,
-                                      void* stream) {
+                                      int out_f16, void* stream) {
     DELORA_CHECK_ARG(x16 && w_stem && y, "delora_stem_fprop_bf16: null pointer");
     DELORA_CHECK_ARG(W % 2 == 0 && W >= 2 && H >= 1 && B >= 1, "delora_stem_fprop_bf16: needs an even image width (got %d)", W);
     DELORA_CHECK_ARG(act >= 0 && act <= 2, "delora_stem_fprop_bf16: act=%d", act);
     StemParams p;
     p.B = B; p.H = H; p.Wout = W / 2; p.segs = (p.Wout + 127) / 128; p.n_jobs = B * H * p.segs; p.act = act;
+    p.out_f16 = out_f16 ? 1 : 0;
     CUtensorMap mx, mw;
     DELORA_CHECK_ARG(stem_encode_x_map(&mx, x16, B, H, W, 128) == 0, "delora_stem_fprop_bf16: tensor map (x) failed");
     {

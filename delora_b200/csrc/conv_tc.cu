@@ -21,6 +21,7 @@
 // circular halo columns).  Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM allocator,
 // 2..5 = epilogue.
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace delora {
@@ -476,9 +477,11 @@ zero_upsample_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, i
 
 // Max-pool with argmax (training): same window as maxpool_nhwc_kernel, additionally stores which of the 9
 // window positions won (first maximum in (row, column) scan order, as PyTorch's backward assumes).
+// `act` != 0: x holds PRE-activations z and the output is act(max z) = max act(z) (tanh / relu are monotonic), so the
+// backward can evaluate act'(z) from z itself -- 1 - a^2 from a bf16-rounded, saturated a = tanh(z) has no correct digit.
 __global__ void __launch_bounds__(256)
 maxpool_idx_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, __nv_bfloat16* __restrict__ y,
-                        uint8_t* __restrict__ idx) {
+                        uint8_t* __restrict__ idx, int act, int in_f16) {
     // one thread = 8 channels of one output pixel: 16-byte loads / stores, 8-byte argmax store
     const int Wout = W / 2, groups = C / 8;
     const size_t total = (size_t)B * H * Wout * groups;
@@ -502,9 +505,10 @@ maxpool_idx_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W
         for (int dq = 0; dq < 3; ++dq) {
             const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * Hp + h + 1) * Wp + 2 * wo + dq) * C) + grp);
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+            const __half2* g2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h2[e]);
+                const float2 f = in_f16 ? __half22float2(g2[e]) : __bfloat1622float2(h2[e]);
                 if (f.x > m[2 * e]) { m[2 * e] = f.x; arg[2 * e] = dr * 3 + dq; }
                 if (f.y > m[2 * e + 1]) { m[2 * e + 1] = f.y; arg[2 * e + 1] = dr * 3 + dq; }
             }
@@ -512,7 +516,7 @@ maxpool_idx_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W
     }
     __nv_bfloat162 o2[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(m[2 * e], m[2 * e + 1]);
+    for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(apply_act(m[2 * e], act), apply_act(m[2 * e + 1], act));
     const uint4 out = *reinterpret_cast<uint4*>(o2);
     const size_t pix = ((size_t)b * Hp + ho + 1) * Wpo + wo + 1;
     reinterpret_cast<uint4*>(y + pix * C)[grp] = out;
@@ -531,7 +535,7 @@ maxpool_idx_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W
 __global__ void __launch_bounds__(256)
 maxpool_bwd_act_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                        const __nv_bfloat16* __restrict__ a, int B, int H, int W, int C, int act,
-                       __nv_bfloat16* __restrict__ dz) {
+                       __nv_bfloat16* __restrict__ dz, int a_f16) {
     // one thread = 8 channels of one input pixel (16-byte accesses)
     const int Wout = W / 2, groups = C / 8;
     const size_t total = (size_t)B * H * W * groups;
@@ -579,12 +583,20 @@ maxpool_bwd_act_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __re
     }
     const uint4 araw = __ldg(reinterpret_cast<const uint4*>(a + (((size_t)b * Hp + h + 1) * Wp + w + 1) * C) + grp);
     const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&araw);
+    const __half2* a2h = reinterpret_cast<const __half2*>(&araw);
     __nv_bfloat162 o2[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float2 av = __bfloat1622float2(a2[e]);
-        const float d0 = (act == 2) ? fmaf(-av.x, av.x, 1.0f) : (act == 1 ? (av.x > 0.0f ? 1.0f : 0.0f) : 1.0f);
-        const float d1 = (act == 2) ? fmaf(-av.y, av.y, 1.0f) : (act == 1 ? (av.y > 0.0f ? 1.0f : 0.0f) : 1.0f);
+        const float2 av = a_f16 ? __half22float2(a2h[e]) : __bfloat1622float2(a2[e]);
+        float d0, d1;
+        if (act == 6) {            // `a` holds pre-activations z: tanh'(z) = 4 e / (1 + e)^2, e = exp(-2 |z|) (no cancellation)
+            const float e0 = __expf(-2.0f * fabsf(av.x)), e1 = __expf(-2.0f * fabsf(av.y));
+            d0 = __fdividef(4.0f * e0, (1.0f + e0) * (1.0f + e0));
+            d1 = __fdividef(4.0f * e1, (1.0f + e1) * (1.0f + e1));
+        } else {
+            d0 = (act == 2) ? fmaf(-av.x, av.x, 1.0f) : ((act == 1 || act == 5) ? (av.x > 0.0f ? 1.0f : 0.0f) : 1.0f);
+            d1 = (act == 2) ? fmaf(-av.y, av.y, 1.0f) : ((act == 1 || act == 5) ? (av.y > 0.0f ? 1.0f : 0.0f) : 1.0f);
+        }
         o2[e] = __floats2bfloat162_rn(g[2 * e] * d0, g[2 * e + 1] * d1);
     }
     const uint4 out = *reinterpret_cast<uint4*>(o2);
@@ -925,21 +937,24 @@ extern "C" int delora_zero_upsample_nhwc_bf16(const void* x, int B, int H, int W
     return 0;
 }
 
-extern "C" int delora_maxpool_w_idx_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* idx, void* stream) {
-    DELORA_CHECK_ARG(x && y && idx && W % 2 == 0 && C % 8 == 0, "delora_maxpool_w_idx_nhwc_bf16: bad argument");
+extern "C" int delora_maxpool_w_idx_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* idx, int act,
+                                              int x_f16, void* stream) {
+    DELORA_CHECK_ARG(x && y && idx && W % 2 == 0 && C % 8 == 0 && act >= 0 && act <= 2,
+                     "delora_maxpool_w_idx_nhwc_bf16: bad argument");
     const size_t total = (size_t)B * H * (W / 2) * (C / 8);
     maxpool_idx_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, B, H, W, C, (__nv_bfloat16*)y, (uint8_t*)idx);
+        (const __nv_bfloat16*)x, B, H, W, C, (__nv_bfloat16*)y, (uint8_t*)idx, act, x_f16 ? 1 : 0);
     DELORA_CHECK_LAUNCH("maxpool_idx_nhwc_kernel");
     return 0;
 }
 
 extern "C" int delora_maxpool_w_bwd_nhwc_bf16(const void* dy, const void* idx, const void* a, int B, int H, int W, int C,
-                                              int act, void* dz, void* stream) {
+                                              int act, void* dz, int a_f16, void* stream) {
     DELORA_CHECK_ARG(dy && idx && a && dz && W % 2 == 0 && C % 8 == 0, "delora_maxpool_w_bwd_nhwc_bf16: bad argument");
     const size_t total = (size_t)B * H * W * (C / 8);
     maxpool_bwd_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy, (const uint8_t*)idx, (const __nv_bfloat16*)a, B, H, W, C, act, (__nv_bfloat16*)dz);
+        (const __nv_bfloat16*)dy, (const uint8_t*)idx, (const __nv_bfloat16*)a, B, H, W, C, act, (__nv_bfloat16*)dz,
+        a_f16 ? 1 : 0);
     DELORA_CHECK_LAUNCH("maxpool_bwd_act_kernel");
     return 0;
 }

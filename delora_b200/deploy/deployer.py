@@ -8,6 +8,12 @@ become one batched device-side pass:
     normals through the pixel->point index map -> encoder -> quaternion -> T (CUDA fwd/bwd) ->
     ONE fused ICP kernel (SE(3) transform, exact NN, po2pl/pl2pl(/po2po), gradient w.r.t. T).
 
+Logging / visualisation (reference :73-89 `create_images`, :316-320 `log_img_2_transformed`,
+:349-356): only when `log_images_bool` is set -- once per epoch in the reference's Trainer -- the first sample is
+additionally run through the list-based ICPLosses operator (kept pairs, pointwise residuals) and its 6- and
+9-channel clouds are projected on the device; a normal step does no extra projection beyond the `visible_pixels`
+coordinates (no image, no sort).
+
 Reference quirks kept on purpose, each behind a config key:
   * `loss_pc` accumulates a running cumulative sum inside the batch loop (:312)
     -> sample j (0-based) gets weight (B - j)/B.  `plain_batch_mean: True` switches to 1/B.
@@ -63,10 +69,27 @@ class Deployer(object):
         self.training_bool = False
         self._scratch = {}
         self.log_img_1, self.log_img_2 = [], []
+        self.log_img_2_transformed = self.log_pointwise_loss = None
+        self.log_normals_target = self.log_normals_transformed_source = None
 
     @staticmethod
     def list_collate(batch_dicts):
         return [batch_dict for batch_dict in batch_dicts]
+
+    def create_images(self, preprocessed_data, losses, plotting):
+        """src/deploy/deployer.py:73-89: images of the target normals and of the transformed source points /
+        normals / pointwise point-to-plane residuals at the kept pairs -- two device-side projections of a
+        6-channel and a 9-channel cloud (the reference: numba + host round trips)."""
+        image_1_at_normals, _, _, _, _ = self.img_projection(
+            input=torch.cat((preprocessed_data["scan_1"], preprocessed_data["normal_list_1"]), dim=1),
+            dataset=preprocessed_data["dataset"])
+        image_2, _, _, _, _ = self.img_projection(
+            input=torch.cat((plotting["scan_2_transformed"], plotting["normals_2_transformed"],
+                             losses["loss_po2pl_pointwise"]), dim=1).detach(),
+            dataset=preprocessed_data["dataset"])
+        self.log_pointwise_loss = image_2[:, 6:9]
+        self.log_normals_target = image_1_at_normals[:, 3:6]
+        self.log_normals_transformed_source = image_2[:, 3:6]
 
     # ---- reference helpers kept for API compatibility (src/deploy/deployer.py:181-189) ----------
     def rotate_point_cloud_transformation_matrix(self, transformation_matrix, point_cloud):
@@ -101,6 +124,8 @@ class Deployer(object):
         return pts, nrm, cnt.to(dev, non_blocking=True)
 
     def _flags(self):
+        if self.config.get("po2po_alone", False):       # :36-46: every source point against its NN, no normals
+            return ops.LOSS_PO2PO
         f = 0
         if self.config["point_to_point_loss"]:
             f |= ops.LOSS_PO2PO
@@ -158,37 +183,66 @@ class Deployer(object):
             return computed_transformations
 
         pts_grid, nrm_grid = ops.grids_from_projection(pts, nrm, index_map)
+        if self.config.get("po2po_alone", False):
+            # the fused kernel takes point-to-point pairs where neither side has a normal: without normals that is
+            # every source point, the reference's po2po_alone branch (src/losses/icp_losses.py:36-46)
+            nrm_grid = torch.zeros_like(nrm_grid)
         key = (b, h * w)
         if key not in self._scratch:
             self._scratch[key] = ops.icp_scratch(b, h * w, pts.device)
         total, parts = _FusedIcp.apply(computed_transformations, pts_grid[b:].contiguous(), nrm_grid[b:].contiguous(),
                                        pts_grid[:b].contiguous(), nrm_grid[:b].contiguous(), (h, w, hf, vf),
                                        float(self.config["lambda_po2pl"]), self._flags(), self._scratch[key])
+        # the reference divides by the CONFIGURED batch size (:329-338), also for a short last batch
+        bs = float(self.batch_size)
         if self.config.get("plain_batch_mean", False):
-            weights = torch.full((b,), 1.0 / b, device=total.device)
-        else:   # running cumulative sum of the reference (:312): sample j is counted (B - j) times, then / B
-            weights = torch.arange(b, 0, -1, device=total.device, dtype=torch.float32) / b
+            weights = torch.full((b,), 1.0 / bs, device=total.device)
+        else:   # running cumulative sum of the reference (:312): sample j is counted (B - j) times, then / batch_size
+            weights = torch.arange(b, 0, -1, device=total.device, dtype=torch.float32) / bs
         losses = {"loss_pc": (weights * total).sum().reshape(1),
-                  "loss_po2po": parts[:, 0].sum().reshape(1) / b,
-                  "loss_po2pl": float(self.config["lambda_po2pl"]) * parts[:, 1].sum().reshape(1) / b,
-                  "loss_pl2pl": parts[:, 2].sum().reshape(1) / b}
+                  "loss_po2po": parts[:, 0].sum().reshape(1) / bs,
+                  "loss_po2pl": float(self.config["lambda_po2pl"]) * parts[:, 1].sum().reshape(1) / bs,
+                  "loss_pl2pl": parts[:, 2].sum().reshape(1) / bs}
         if not self.config["unsupervised_at_start"]:                        # identity fitting (:324-327, :334-336)
             eye = torch.eye(4, device=total.device).view(1, 4, 4)
-            loss = self.lossTransformation(input=computed_transformations[-1:], target=eye) / b
+            loss = self.lossTransformation(input=computed_transformations[-1:], target=eye) / bs
         else:
             loss = losses["loss_pc"]
         if self.training_bool:
             loss.sum().backward()
             self.optimizer.step()
+        if epoch_losses is not None:
+            # `visible_pixels` (:365-367): points of a transformed source scan with 0 < v < H, projected with the
+            # transform BEFORE the translation is rescaled (:344-346 comes after the transform of :294 in the reference).
+            # Normal steps: the LAST sample (the reference's loop variable, :349-352); log steps: the FIRST (:317-319).
+            with torch.no_grad():
+                k = 0 if log_images_bool else b - 1
+                n_k = int((batch.counts_host if padded else [d["scan_1"].shape[2] for d in preprocessed_dicts]
+                           + [d["scan_2"].shape[2] for d in preprocessed_dicts])[b + k])
+                src = pts[b + k:b + k + 1, :, :n_k]
+                t_k = computed_transformations[k:k + 1].detach()
+                moved = self.transform_point_cloud_transformation_matrix(t_k, src).contiguous()
+                if log_images_bool and not self.config.get("po2po_alone", False):
+                    # logging path (once per epoch): image of the transformed source scan (:316-320), then the list-
+                    # based loss operator on sample 0 for the kept pairs and the pointwise residuals (:302-307), then
+                    # the two multi-channel projections of create_images (:353-356)
+                    self.log_img_2_transformed, _, v_all, _, _ = self.img_projection(input=moved, dataset=dataset)
+                    v_pix = v_all
+                    n_1 = int((batch.counts_host if padded else [d["scan_1"].shape[2] for d in preprocessed_dicts])[0])
+                    tgt, tgt_n = pts[0:1, :, :n_1].contiguous(), nrm[0:1, :, :n_1].contiguous()
+                    src_n = self.rotate_point_cloud_transformation_matrix(t_k, nrm[b:b + 1, :, :n_k]).contiguous()
+                    losses_0, plotting_0 = self.lossPointCloud(
+                        source_point_cloud_transformed=moved, source_normal_list_transformed=src_n,
+                        target_point_cloud=tgt, target_normal_list=tgt_n, compute_pointwise_loss_bool=True)
+                    losses["loss_po2pl_pointwise"] = losses_0["loss_po2pl_pointwise"]
+                    self.create_images(preprocessed_data={"scan_1": tgt, "normal_list_1": tgt_n, "dataset": dataset},
+                                       losses=losses, plotting=plotting_0)
+                else:
+                    _, v_pix, _ = ops.project_uv(moved, cnt[b + k:b + k + 1].contiguous(), h, w, hf, vf)
+                visible = ((torch.round(v_pix[0, :n_k]) < h) & (v_pix[0, :n_k] > 0)).sum()
         if scaling is not None:
             computed_transformations[:, :3, 3] *= scaling.view(b, 1)
         if epoch_losses is not None:
-            # `visible_pixels` (:365-367): points of the last transformed source scan with 0 < v < H
-            with torch.no_grad():
-                src = pts[2 * b - 1:2 * b, :, :n_last]
-                moved = self.transform_point_cloud_transformation_matrix(computed_transformations[-1:].detach(), src)
-                _, v_pix, _ = ops.project_uv(moved.contiguous(), cnt[2 * b - 1:2 * b].contiguous(), h, w, hf, vf)
-                visible = ((torch.round(v_pix[0, :n_last]) < h) & (v_pix[0, :n_last] > 0)).sum()
             epoch_losses["loss_epoch"] += loss.detach().cpu().numpy()
             epoch_losses["loss_point_cloud_epoch"] += losses["loss_pc"].detach().cpu().numpy()
             epoch_losses["loss_po2po_epoch"] += losses["loss_po2po"].detach().cpu().numpy()

@@ -238,14 +238,16 @@ class TensorCoreEncoder:
         return params
 
     def trunk_parameter_groups(self):
-        """Trunk parameter indices grouped in the order the backward finishes them: layer4, layer3, the rest."""
+        """Trunk parameter indices grouped in the order the backward finishes them: layer4, layer3, layer2,
+        layer1 + stem (the last, exposed bucket is the smallest: 0.15 M parameters)."""
         nb = len(self.blocks)
         per_layer = nb // 4 if nb % 4 == 0 and nb >= 4 else None
         if per_layer is None:
             return [[i for blk in reversed(self._block_param_idx) for i in blk] + [0]]
         def blocks(lo, hi):
             return [i for b in range(hi - 1, lo - 1, -1) for i in self._block_param_idx[b]]
-        return [blocks(3 * per_layer, nb), blocks(2 * per_layer, 3 * per_layer), blocks(0, 2 * per_layer) + [0]]
+        return [blocks(3 * per_layer, nb), blocks(2 * per_layer, 3 * per_layer), blocks(per_layer, 2 * per_layer),
+                blocks(0, per_layer) + [0]]
 
     def _gout(self, index):
         return self.grad_views[index] if self.grad_views is not None else None
@@ -271,18 +273,22 @@ class TensorCoreEncoder:
         stem_w, blk_w = self._block_weights(self._refresh_weights(force=True))    # bf16 filters of THIS step's weights
         w2 = ops.conv_out_size(w, 2)
         st["stem_fast"] = self._stem_fast(w)
+        # the stem stores its PRE-activation z; the pool applies the activation to the maximum (tanh / relu are
+        # monotonic) and the backward evaluates act'(z) from z (exact for saturated units, see maxpool_bwd_act_kernel)
         if st["stem_fast"]:
             st["x_in"] = ops.images_to_nhwc16(image_1, image_2)
-            st["y0"] = ops.stem_fprop(st["x_in"], self._wstem, h, w, self.act, self._buffer("t_stem", b, h, w2, 64, dev, sid))
+            st["y0"] = ops.stem_fprop(st["x_in"], self._wstem, h, w, ops.ACT_NONE, self._buffer("t_stem", b, h, w2, 64, dev, sid),
+                                      out_f16=True)       # fp16 pre-activation: only the two pool kernels read it
         else:
             st["x_in"] = ops.images_to_nhwc(image_1, image_2, 64)
-            st["y0"] = ops.conv2d_fprop(st["x_in"], stem_w[0], h, w, 3, (1, 2), self.act, None,
+            st["y0"] = ops.conv2d_fprop(st["x_in"], stem_w[0], h, w, 3, (1, 2), ops.ACT_NONE, None,
                                         self._buffer("t_stem", b, h, w2, 64, dev, sid))
         w4 = w2 // 2
         st["p0"] = self._buffer("t_pool", b, h, w4, 64, dev, sid)
         st["idx"] = torch.empty((b, h, w4, 64), dtype=torch.uint8, device=dev)
         ops._lib.check(L.delora_maxpool_w_idx_nhwc_bf16(st["y0"].data_ptr(), b, h, w2, 64, st["p0"].data_ptr(),
-                                                        st["idx"].data_ptr(), ops._stream()),
+                                                        st["idx"].data_ptr(), 1 if self.act == ops.ACT_RELU else 2,
+                                                        1 if st["stem_fast"] else 0, ops._stream()),
                        "delora_maxpool_w_idx_nhwc_bf16")
         cur, ch, cw = st["p0"], h, w4
         for i, blk in enumerate(self.blocks):
@@ -365,7 +371,8 @@ class TensorCoreEncoder:
         w2 = ops.conv_out_size(w, 2)
         dz0 = self._buffer("g_stem", b, h, w2, 64, dev)
         ops._lib.check(L.delora_maxpool_w_bwd_nhwc_bf16(d_pool.data_ptr(), st["idx"].data_ptr(), st["y0"].data_ptr(), b, h,
-                                                        w2, 64, act_id, dz0.data_ptr(), ops._stream()),
+                                                        w2, 64, 4 + act_id, dz0.data_ptr(), 1 if st["stem_fast"] else 0,
+                                                        ops._stream()),
                        "delora_maxpool_w_bwd_nhwc_bf16")
         if st["stem_fast"]:
             g_stem = ops.stem_wgrad(st["x_in"], dz0, h, w, st["w_stem"].shape[1], out=self._gout(0))

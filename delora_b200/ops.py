@@ -423,14 +423,16 @@ def stem_weight_prep(weight, w_stem):
     return w_stem
 
 
-def stem_fprop(x16, w_stem, h, w, act, out=None):
-    """x16 [B,H+2,W+2,16], w_stem [3,64,64] -> y [B,H+2,W/2+2,64] (3x3, stride (1,2), activation)."""
+def stem_fprop(x16, w_stem, h, w, act, out=None, out_f16=False):
+    """x16 [B,H+2,W+2,16], w_stem [3,64,64] -> y [B,H+2,W/2+2,64] (3x3, stride (1,2), activation).
+    out_f16: the (bf16-typed) output buffer receives fp16 bit patterns (training: pre-activation for the pool kernels)."""
     b = x16.shape[0]
     if out is None:
         out = padded_nhwc_zeros(b, h, w // 2, 64, x16.device)
     L = _lib.lib()
     _lib.check(L.delora_stem_fprop_bf16(_req(x16, torch.bfloat16, "x16"), _req(w_stem, torch.bfloat16, "w_stem"),
-                                        out.data_ptr(), b, h, w, int(act), _stream()), "delora_stem_fprop_bf16")
+                                        out.data_ptr(), b, h, w, int(act), 1 if out_f16 else 0, _stream()),
+               "delora_stem_fprop_bf16")
     return out
 
 

@@ -5,7 +5,7 @@ only collective of the training step.  One process per GPU, launched with torchr
 
 `BucketedGradAllReduce` (the training path): every gradient is a view of ONE persistent flat fp32 buffer (11.88 M
 elements = 47.5 MB for the default model) laid out in BACKWARD order as a few buckets (heads + fc | layer4 | layer3 |
-layer2 + layer1 + stem).  The tensor-core encoder writes its weight gradients straight into the flat slices (no copies)
+layer2 | layer1 + stem).  The tensor-core encoder writes its weight gradients straight into the flat slices (no copies)
 and announces each group from inside its backward, so NCCL reduces layer4 (33.6 MB) on its own stream while the
 backward of layers 3 -> 1 still runs; only the last small bucket is exposed.  `FlatGradAllReduce` (one blocking
 all-reduce after backward) is kept for the CPU / gloo tests and as the measured baseline of the overlap."""

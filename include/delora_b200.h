@@ -291,10 +291,12 @@ int delora_conv_weight_prep_multi(const void* table, int n_layers, void* stream)
  * x16    [B, H+2, W+2, 16] bf16: channels 0..7 = cat(image_1, image_2) (src/models/model.py:98), 8..15 zero, padding
  *        materialised as everywhere (delora_images_to_nhwc16_bf16 writes it)
  * w_stem [3, 64, 64] bf16: [filter row][output channel][k = q * 16 + c] (delora_stem_weight_prep_bf16)
- * y      [B, H+2, W/2+2, 64] bf16 out;  dz same shape;  dw [64, Cin_true, 3, 3] fp32.  W must be even. */
+ * y      [B, H+2, W/2+2, 64] bf16 out (fp16 bit patterns when out_f16 = 1);  dz same shape;  dw [64, Cin_true, 3, 3]
+ *        fp32.  W must be even. */
 int delora_images_to_nhwc16_bf16(const float* image_1, const float* image_2, int B, int H, int W, void* x16, void* stream);
 int delora_stem_weight_prep_bf16(const float* w, int Cin, void* w_stem, void* stream);
-int delora_stem_fprop_bf16(const void* x16, const void* w_stem, void* y, int B, int H, int W, int act, void* stream);
+int delora_stem_fprop_bf16(const void* x16, const void* w_stem, void* y, int B, int H, int W, int act, int out_f16,
+                           void* stream);
 int64_t delora_stem_wgrad_scratch_floats(int B, int H, int W);
 int delora_stem_wgrad_bf16(const void* x16, const void* dz, float* dw, float* scratch, int B, int H, int W, int Cin_true,
                            void* stream);
@@ -306,10 +308,17 @@ int delora_images_to_nhwc_bf16(const float* image_1, const float* image_2, int B
 int delora_maxpool_w_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* stream);
 /* training variants of the pools: forward with argmax (idx: uint8 [B,H,W/2,C]); backward of the max-pool
  * fused with act'(a) of the stem activation a; backward of the global average pool fused with act'(a) of
- * the last block (g: [B,C] fp32).  act: 0 none, 1 relu, 2 tanh.  All tensors padded NHWC bf16. */
-int delora_maxpool_w_idx_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* idx, void* stream);
+ * the last block (g: [B,C] fp32).  act: 0 none, 1 relu, 2 tanh.  All tensors padded NHWC bf16.
+ * Pre-activation form (what the training path uses for the stem): the forward pool takes the stem's PRE-activation
+ * z and applies `act` to the maximum (max act(z) = act(max z) for the monotonic tanh / relu); the backward then gets
+ * `a` = z and act = 5 (relu'(z)) or 6 (tanh'(z) = 4 e^{-2|z|} / (1 + e^{-2|z|})^2): 1 - a^2 evaluated on a bf16-rounded,
+ * saturated tanh output has no correct digit, the metre-valued inputs saturate the stem heavily.
+ * x_f16 / a_f16 = 1: that tensor holds fp16 instead of bf16 values (delora_stem_fprop_bf16 with out_f16 = 1): three more
+ * mantissa bits keep the pool's argmax on the fp32 winner when two window entries nearly tie. */
+int delora_maxpool_w_idx_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* idx, int act, int x_f16,
+                                   void* stream);
 int delora_maxpool_w_bwd_nhwc_bf16(const void* dy, const void* idx, const void* a, int B, int H, int W, int C, int act,
-                                   void* dz, void* stream);
+                                   void* dz, int a_f16, void* stream);
 int delora_avgpool_bwd_nhwc_bf16(const float* g, const void* a, int B, int H, int W, int C, int act, void* dz,
                                  void* stream);
 /* padded NHWC bf16 -> NCHW fp32 (interior), the reference's feature-map layout */

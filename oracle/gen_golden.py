@@ -231,6 +231,45 @@ def preprocess_golden():
               "normals", np.array_equal(normals.numpy(), out[f"normals_{k}"]), out[f"points_{k}"].shape)
 
 
+def log_images_golden():
+    """The logging / visualisation projections of the training step (src/deploy/deployer.py:73-89 create_images,
+    :316-320 log_img_2_transformed): the reference's own Deployer.create_images on the small case, fed by its
+    ICPLosses with compute_pointwise_loss_bool=True."""
+    torch.set_num_threads(1)
+    ref = ref_harness.reference_modules()
+    import deploy.deployer
+    idx, w_raw, rings, vfov, h, w = CASES["small_16x180"]
+    cfg = synthetic.fov_config(h=h, w=w, vfov_deg=vfov)
+    scan_1, scan_2, _, t_pred = synthetic.make_pair(idx, w_raw=w_raw, rings=rings, vfov_deg=vfov)
+    proj = ref.projection.ImageProjectionLayer(config=cfg)
+    nc = ref.normal_computation.NormalsComputer(config=cfg, dataset_name="kitti")
+    lists = []
+    for scan in (scan_1, scan_2):
+        image = proj(input=scan[None].clone(), dataset="kitti")[0]
+        normals, _, points = nc.compute_normal_vectors(image=image.clone())
+        lists.append((points.t()[None].contiguous(), normals.t()[None].contiguous()))
+    (p1, n1), (p2, n2) = lists
+    dep = object.__new__(deploy.deployer.Deployer)
+    dep.config, dep.img_projection = cfg, proj
+    tm = t_pred.clone().view(1, 4, 4)
+    src = dep.transform_point_cloud_transformation_matrix(transformation_matrix=tm, point_cloud=p2)
+    src_n = dep.rotate_point_cloud_transformation_matrix(transformation_matrix=tm, point_cloud=n2)
+    icp = ref.icp_losses.ICPLosses(config=cfg)
+    losses, plotting = icp(source_point_cloud_transformed=src, source_normal_list_transformed=src_n,
+                           target_point_cloud=p1, target_normal_list=n1, compute_pointwise_loss_bool=True)
+    img_2_t, _, v_pixel, _, _ = proj(input=src, dataset="kitti")
+    dep.create_images(preprocessed_data={"scan_1": p1, "normal_list_1": n1, "dataset": "kitti"}, losses=losses,
+                      plotting=plotting)
+    out = {"points_1": p1[0].numpy(), "normals_1": n1[0].numpy(), "points_2": p2[0].numpy(), "normals_2": n2[0].numpy(),
+           "t_pred": t_pred.numpy(), "log_img_2_transformed": img_2_t[0].numpy(),
+           "log_pointwise_loss": dep.log_pointwise_loss[0].detach().numpy(),
+           "log_normals_target": dep.log_normals_target[0].numpy(),
+           "log_normals_transformed_source": dep.log_normals_transformed_source[0].detach().numpy(),
+           "visible_pixels": np.array([int(((torch.round(v_pixel) < h) & (v_pixel > 0)).sum())])}
+    np.savez_compressed(os.path.join(GOLDEN, "log_images_16x180.npz"), **out)
+    print("log images", {k: v.shape for k, v in out.items()})
+
+
 def poses_golden():
     """Pose chaining (src/utility/poses.py:11-58) of 40 slightly non-orthonormal relative transforms."""
     ref_harness.install()
@@ -253,9 +292,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--poses-only":
         poses_golden()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--log-images-only":
+        log_images_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--preprocess-only":
         preprocess_golden()
         sys.exit(0)
     main()
     preprocess_golden()
+    log_images_golden()
     poses_golden()

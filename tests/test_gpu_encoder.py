@@ -169,7 +169,7 @@ def test_encoder_training_path_gradients(h, w, cuda_lib):
     (pooled * sel).sum().backward()
     cosines = [F.cosine_similarity(p.grad.flatten(), r.flatten(), dim=0).item()
                for p, r in zip(enc.trunk_parameters(), ref)]
-    assert len(cosines) == 20 and min(cosines[1:]) > 0.999 and cosines[0] > 0.98, cosines
+    assert len(cosines) == 20 and min(cosines[1:]) > 0.999 and cosines[0] > 0.99, cosines   # stem: see test_gpu_sizes.py
     # model-level: training forward with the flag goes through the differentiable tcgen05 trunk
     model.config["use_tensor_core_encoder"] = True
     model.zero_grad()

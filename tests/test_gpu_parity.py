@@ -2,8 +2,8 @@
 
 Bars: bit-exact for integer / index work (winner selection, index maps, lists, counts, NN
 indices, sort order); fp32 losses within 1e-5 rel of the oracle (BASELINE.json north_star);
-the 12-float transform gradient within 1e-4 of its max-abs entry; normals within a
-conditioning-aware tolerance (see test_normals)."""
+the 12-float transform gradient within 1e-5 of its max-abs entry; normals p99 <= 1e-6 and max <= 5e-5
+against the reference's LAPACK eigenvectors (see test_normals_and_lists)."""
 import math
 import os
 
@@ -192,8 +192,10 @@ def test_normals_and_lists(name, golden, cuda_lib):
         print(f"[{name}/normals_{k}] P={p} with normal={int(has_o.sum())} |dn| median={q[0]:.2e} "
               f"p99={q[1]:.2e} p99.9={q[2]:.2e} max={err.max().item():.2e} unit err={unit:.1e}")
         assert unit < 1e-5
-        assert q[1] < 2e-4, "99% of the normals must agree with the reference to 2e-4"
-        assert (err > 1e-2).float().mean().item() < 2e-3, "ill-conditioned outliers must stay rare"
+        # measured on B200 (scripts/gpu_normals_stats.py, six image sizes): p99 <= 4.3e-7, max <= 1.14e-5 (at an
+        # eigen-gap of 1e-3 of the largest eigenvalue, where LAPACK's own fp32 result is no better determined)
+        assert q[1] <= 1e-6, "99% of the normals must agree with the reference's LAPACK result to 1e-6"
+        assert err.max().item() <= 5e-5, "every normal within 5e-5"
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -258,7 +260,7 @@ def test_pair_pipeline_end_to_end(name, golden, cuda_lib):
     # with the SLEEF-exact atan2 the projection reproduces the CPU reference's pixels, so the whole chain
     # meets the 1e-5 bar against the REFERENCE's own numbers (not only against the oracle on equal inputs)
     assert int(losses[0, 3]) == meta["num_pairs"]
-    assert rel_pl < 1e-5 and rel_nn < 1e-5 and gerr < 1e-4
+    assert rel_pl < 1e-5 and rel_nn < 1e-5 and gerr < 1e-5
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -279,7 +281,7 @@ def test_dense_icp_matches_list_icp(name, golden, cuda_lib):
     assert row[1].item() == pytest.approx(out["loss_po2pl"], rel=1e-5)
     assert row[2].item() == pytest.approx(out["loss_pl2pl"], rel=1e-5)
     g_ref = out["grad_T"].numpy()
-    assert np.abs(grad_t[0].cpu().numpy().reshape(3, 4) - g_ref).max() <= 1e-4 * np.abs(g_ref).max()
+    assert np.abs(grad_t[0].cpu().numpy().reshape(3, 4) - g_ref).max() <= 1e-5 * np.abs(g_ref).max()
     # CSR kernel on the lists of the same images: same pair count, same sums up to summation order
     nrm_img = ops.normals(images)
     pts4, nrm4, cs, counts = ops.lists_from_images(images, nrm_img)
