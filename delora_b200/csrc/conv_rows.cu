@@ -250,70 +250,99 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const RowsJob j = rows_decode(p, job, CG);
             const RowsPhase& ph = p.phase[j.ph];
             const uint32_t ab = j_it & 1;
-            mbar_wait(acc_full + ab, (j_it >> 1) & 1);
-            tc_fence_after();
+            // Both epilogue forms walk the job's 32-column accumulator blocks with the residual / saved loads of block
+            // k + 1 in flight while block k is read from TMEM and stored (and block 0's loads issued before the
+            // accumulators are even complete): the epilogue was stalled on exactly these global loads (ncu: the bf16
+            // unpack after the residual load held 25 % of all samples, the tensor pipe idled behind acc_empty).
+            struct Blk { size_t off, roff; bool in_range, use_res, hl, hr; };
             if (PIXM) {
                 // lane = pixel of the segment, columns = output channels: no transpose
                 const int wl = quarter * 32 + lane, wg = j.w0 + wl;
                 const int wo = wg * p.out_sw + ph.ow;
-                for (int i = 0; i < p.R; ++i) {
+                const int cpb = p.n_tile >> 5, nb = p.R * cpb;
+                auto info = [&](int k) {
+                    Blk bi;
+                    const int i = k / cpb, c0 = (k - i * cpb) << 5;
                     const int hg = j.h0 + (int)rank * p.R + i;
                     const int ho = hg * p.out_sh + ph.oh;
-                    const bool in_range = hg < p.Hg && wg < p.Wg && ho < p.Hout && wo < p.Wout;
-                    const bool use_res = residual != nullptr && (!p.res_grid || (ph.oh | ph.ow) == 0);
-                    for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-                        const int c_first = j.ct * p.n_tile + c0;
-                        const size_t off = (((size_t)j.b * Hp + (ho + 1)) * Wp + (wo + 1)) * p.Cout + c_first;
-                        const size_t roff = p.res_grid
-                            ? (((size_t)j.b * (p.Hg + 2) + (hg + 1)) * (p.Wg + 2) + (wg + 1)) * p.Cout + c_first : off;
-                        EpiloguePrefetch pf;
-                        if (in_range)
-                            epilogue_prefetch32(pf, use_res ? residual + roff : nullptr, saved + (p.act >= 3 ? off : 0), 0, p.act);
-                        uint32_t acc[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * 256 + (uint32_t)(i * p.n_tile + c0), acc);
-                        if (in_range) {
-                            float v[32];
+                    bi.in_range = hg < p.Hg && wg < p.Wg && ho < p.Hout && wo < p.Wout;
+                    bi.use_res = residual != nullptr && (!p.res_grid || (ph.oh | ph.ow) == 0);
+                    const int c_first = j.ct * p.n_tile + c0;
+                    bi.off = (((size_t)j.b * Hp + (ho + 1)) * Wp + (wo + 1)) * p.Cout + c_first;
+                    bi.roff = p.res_grid ? (((size_t)j.b * (p.Hg + 2) + (hg + 1)) * (p.Wg + 2) + (wg + 1)) * p.Cout + c_first
+                                         : bi.off;
+                    bi.hr = wo == 0; bi.hl = wo == p.Wout - 1;
+                    return bi;
+                };
+                Blk bn = info(0);
+                EpiloguePrefetch nxt;
+                if (bn.in_range)
+                    epilogue_prefetch32(nxt, bn.use_res ? residual + bn.roff : nullptr, saved + (p.act >= 3 ? bn.off : 0), 0, p.act);
+                mbar_wait(acc_full + ab, (j_it >> 1) & 1);
+                tc_fence_after();
+                for (int k = 0; k < nb; ++k) {
+                    const Blk bc = bn;
+                    const EpiloguePrefetch cur = nxt;
+                    if (k + 1 < nb) {
+                        bn = info(k + 1);
+                        if (bn.in_range)
+                            epilogue_prefetch32(nxt, bn.use_res ? residual + bn.roff : nullptr, saved + (p.act >= 3 ? bn.off : 0), 0, p.act);
+                    }
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * 256 + (uint32_t)(k << 5), acc);
+                    if (bc.in_range) {
+                        float v[32];
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]);
-                            epilogue_finish32(v, pf, use_res, y, off, p.act, wo == 0, wo == p.Wout - 1, (size_t)p.Wout * p.Cout);
-                        }
+                        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]);
+                        epilogue_finish32(v, cur, bc.use_res, y, bc.off, p.act, bc.hr, bc.hl, (size_t)p.Wout * p.Cout);
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) { if (CG == 2) mbar_arrive_leader(acc_empty + ab); else mbar_arrive(acc_empty + ab); }
-                continue;
-            }
-            const int c_first = (j.ct * CG + (int)rank) * 128 + quarter * 32;
-            for (int cb = 0; cb < n_blocks; ++cb) {
-                // this thread's pixel of the block; its residual / saved loads go out before the TMEM read
-                // accumulator column -> (row i of the job, CTA half, pixel): columns of MMA i are [i][half][NS]
-                const int col = cb * 32 + lane;
-                const int blk = col / p.NS, wl = col - blk * p.NS;
-                const int i = blk / CG, half = blk - i * CG;
-                const int hg = j.h0 + half * p.R + i, wg = j.w0 + wl;
-                const int ho = hg * p.out_sh + ph.oh, wo = wg * p.out_sw + ph.ow;
-                const bool in_range = hg < p.Hg && wg < p.Wg && ho < p.Hout && wo < p.Wout;
-                const size_t off = (((size_t)j.b * Hp + (ho + 1)) * Wp + (wo + 1)) * p.Cout + c_first;
-                const bool use_res = residual != nullptr && (!p.res_grid || (ph.oh | ph.ow) == 0);
-                const size_t roff = p.res_grid
-                    ? (((size_t)j.b * (p.Hg + 2) + (hg + 1)) * (p.Wg + 2) + (wg + 1)) * p.Cout + c_first : off;
-                EpiloguePrefetch pf;
-                if (in_range) epilogue_prefetch32(pf, use_res ? residual + roff : nullptr, saved + (p.act >= 3 ? off : 0), 0, p.act);
-                uint32_t acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * 256 + (uint32_t)(cb * 32), acc);
-                // transpose: thread = channel `lane` holds 32 pixels -> thread = pixel `lane` holds 32 channels.
-                // XOR-swizzled 32 x 32 fp32 tile: both directions are bank-conflict free
+            } else {
+                const int c_first = (j.ct * CG + (int)rank) * 128 + quarter * 32;
+                auto info = [&](int cb) {
+                    // accumulator column -> (row i of the job, CTA half, pixel): columns of MMA i are [i][half][NS]
+                    Blk bi;
+                    const int col = cb * 32 + lane;
+                    const int blk = col / p.NS, wl = col - blk * p.NS;
+                    const int i = blk / CG, half = blk - i * CG;
+                    const int hg = j.h0 + half * p.R + i, wg = j.w0 + wl;
+                    const int ho = hg * p.out_sh + ph.oh, wo = wg * p.out_sw + ph.ow;
+                    bi.in_range = hg < p.Hg && wg < p.Wg && ho < p.Hout && wo < p.Wout;
+                    bi.use_res = residual != nullptr && (!p.res_grid || (ph.oh | ph.ow) == 0);
+                    bi.off = (((size_t)j.b * Hp + (ho + 1)) * Wp + (wo + 1)) * p.Cout + c_first;
+                    bi.roff = p.res_grid ? (((size_t)j.b * (p.Hg + 2) + (hg + 1)) * (p.Wg + 2) + (wg + 1)) * p.Cout + c_first
+                                         : bi.off;
+                    bi.hr = wo == 0; bi.hl = wo == p.Wout - 1;
+                    return bi;
+                };
+                Blk bn = info(0);
+                EpiloguePrefetch nxt;
+                if (bn.in_range)
+                    epilogue_prefetch32(nxt, bn.use_res ? residual + bn.roff : nullptr, saved + (p.act >= 3 ? bn.off : 0), 0, p.act);
+                mbar_wait(acc_full + ab, (j_it >> 1) & 1);
+                tc_fence_after();
+                for (int cb = 0; cb < n_blocks; ++cb) {
+                    const Blk bc = bn;
+                    const EpiloguePrefetch cur = nxt;
+                    if (cb + 1 < n_blocks) {
+                        bn = info(cb + 1);
+                        if (bn.in_range)
+                            epilogue_prefetch32(nxt, bn.use_res ? residual + bn.roff : nullptr, saved + (p.act >= 3 ? bn.off : 0), 0, p.act);
+                    }
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * 256 + (uint32_t)(cb * 32), acc);
+                    // transpose: thread = channel `lane` holds 32 pixels -> thread = pixel `lane` holds 32 channels.
+                    // XOR-swizzled 32 x 32 fp32 tile: both directions are bank-conflict free
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) st[jj * 32 + (lane ^ jj)] = __uint_as_float(acc[jj]);
-                __syncwarp();
-                float v[32];
+                    for (int jj = 0; jj < 32; ++jj) st[jj * 32 + (lane ^ jj)] = __uint_as_float(acc[jj]);
+                    __syncwarp();
+                    float v[32];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = st[lane * 32 + (c ^ lane)];
-                __syncwarp();
-                if (in_range)
-                    epilogue_finish32(v, pf, use_res, y, off, p.act, wo == 0, wo == p.Wout - 1,
-                                      (size_t)p.Wout * p.Cout);
+                    for (int c = 0; c < 32; ++c) v[c] = st[lane * 32 + (c ^ lane)];
+                    __syncwarp();
+                    if (bc.in_range)
+                        epilogue_finish32(v, cur, bc.use_res, y, bc.off, p.act, bc.hr, bc.hl, (size_t)p.Wout * p.Cout);
+                }
             }
             tc_fence_before();
             __syncwarp();

@@ -550,37 +550,52 @@ maxpool_bwd_act_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __re
     float g[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) g[e] = 0.0f;
-    // padded columns that hold this input column: w+1 always; 0 if w == W-1; W+1 if w == 0
-    for (int alias = 0; alias < 3; ++alias) {
-        int wp;
-        if (alias == 0) wp = w + 1;
-        else if (alias == 1) { if (w != W - 1) continue; wp = 0; }
-        else { if (w != 0) continue; wp = W + 1; }
-        for (int dq = 0; dq < 3; ++dq) {                 // window column offset: wp = 2*wo + dq
-            const int t = wp - dq;
-            if (t < 0 || (t & 1)) continue;
-            const int wo = t >> 1;
-            if (wo >= Wout) continue;
-            for (int dr = 0; dr < 3; ++dr) {             // window row offset: h = ho + dr - 1
-                const int ho = h - dr + 1;
-                if (ho < 0 || ho >= H) continue;
-                const uint2 am = __ldg(reinterpret_cast<const uint2*>(idx + (((size_t)b * H + ho) * Wout + wo) * C) + grp);
-                const unsigned want = (unsigned)(dr * 3 + dq) * 0x01010101u;
-                const unsigned eq_lo = am.x ^ want, eq_hi = am.y ^ want;      // a zero byte = this window's argmax is (h, w)
-                if ((((eq_lo - 0x01010101u) & ~eq_lo) | ((eq_hi - 0x01010101u) & ~eq_hi)) & 0x80808080u) {
-                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(dy + (((size_t)b * Hp + ho + 1) * Wpo + wo + 1) * C) + grp);
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    // Windows that contain input column w: padded column wp = 2 wo + dq.  wp = w + 1 always; the circular halo adds
+    // wp = 0 for w == W - 1 (wp = W + 1 for w == 0 would need wo = Wout: outside).  At most 3 (wo, dq) candidates x 3
+    // rows = 9 windows; all argmax words are loaded first (independent 8-byte loads), then the matching dy rows.
+    int c_wo[3], c_dq[3];
+    int nc = 0;
+    {
+        const int wp = w + 1;
+        if (wp & 1) { c_wo[nc] = (wp - 1) >> 1; c_dq[nc] = 1; ++nc; }
+        else {
+            c_wo[nc] = wp >> 1; c_dq[nc] = 0; ++nc;
+            c_wo[nc] = (wp >> 1) - 1; c_dq[nc] = 2; ++nc;
+        }
+        if (w == W - 1) { c_wo[nc] = 0; c_dq[nc] = 0; ++nc; }              // halo copy at padded column 0
+    }
+    uint2 am[9];
+    bool ok[9];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 f = __bfloat1622float2(h2[e]);
-                        const unsigned word = (e < 2) ? eq_lo : eq_hi;
-                        if (((word >> (16 * (e & 1))) & 0xffu) == 0u) g[2 * e] += f.x;
-                        if (((word >> (16 * (e & 1) + 8)) & 0xffu) == 0u) g[2 * e + 1] += f.y;
-                    }
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int dr = 0; dr < 3; ++dr) {
+            const int ho = h - dr + 1;
+            const bool valid = ci < nc && ho >= 0 && ho < H && c_wo[ci < nc ? ci : 0] < Wout;
+            ok[ci * 3 + dr] = valid;
+            am[ci * 3 + dr] = valid ? __ldg(reinterpret_cast<const uint2*>(idx + (((size_t)b * H + ho) * Wout + c_wo[ci]) * C) + grp)
+                                    : make_uint2(0xffffffffu, 0xffffffffu);
+        }
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int dr = 0; dr < 3; ++dr) {
+            if (!ok[ci * 3 + dr]) continue;
+            const unsigned want = (unsigned)(dr * 3 + c_dq[ci]) * 0x01010101u;
+            const unsigned eq_lo = am[ci * 3 + dr].x ^ want, eq_hi = am[ci * 3 + dr].y ^ want;   // zero byte = argmax is (h, w)
+            if ((((eq_lo - 0x01010101u) & ~eq_lo) | ((eq_hi - 0x01010101u) & ~eq_hi)) & 0x80808080u) {
+                const int ho = h - dr + 1;
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(dy + (((size_t)b * Hp + ho + 1) * Wpo + c_wo[ci] + 1) * C) + grp);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    const unsigned word = (e < 2) ? eq_lo : eq_hi;
+                    if (((word >> (16 * (e & 1))) & 0xffu) == 0u) g[2 * e] += f.x;
+                    if (((word >> (16 * (e & 1) + 8)) & 0xffu) == 0u) g[2 * e + 1] += f.y;
                 }
             }
         }
-    }
     const uint4 araw = __ldg(reinterpret_cast<const uint4*>(a + (((size_t)b * Hp + h + 1) * Wp + w + 1) * C) + grp);
     const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&araw);
     const __half2* a2h = reinterpret_cast<const __half2*>(&araw);
@@ -611,21 +626,35 @@ maxpool_bwd_act_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __re
 __global__ void __launch_bounds__(256)
 avgpool_bwd_act_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ a, int B, int H, int W, int C,
                        int act, __nv_bfloat16* __restrict__ dz) {
-    const size_t total = (size_t)B * H * W * C;
+    // one thread = 8 channels of one pixel (16-byte accesses)
+    const int groups = C / 8;
+    const size_t total = (size_t)B * H * W * groups;
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= total) return;
-    const int c = (int)(i % C);
-    size_t r = i / C;
+    const int grp = (int)(i % groups);
+    size_t r = i / groups;
     const int w = (int)(r % W); r /= W;
     const int h = (int)(r % H);
     const int b = (int)(r / H);
     const size_t pix = ((size_t)b * (H + 2) + h + 1) * (W + 2) + w + 1;
-    const float av = __bfloat162float(a[pix * C + c]);
-    const float d = (act == 2) ? fmaf(-av, av, 1.0f) : (act == 1 ? (av > 0.0f ? 1.0f : 0.0f) : 1.0f);
-    const __nv_bfloat16 o = __float2bfloat16_rn(g[(size_t)b * C + c] / (float)(H * W) * d);
-    dz[pix * C + c] = o;
-    if (w == 0) dz[(pix + W) * C + c] = o;
-    if (w == W - 1) dz[(pix - W) * C + c] = o;
+    const uint4 araw = __ldg(reinterpret_cast<const uint4*>(a + pix * C) + grp);
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&araw);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + (size_t)b * C + grp * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + (size_t)b * C + grp * 8) + 1);
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float inv = 1.0f / (float)(H * W);
+    __nv_bfloat162 o2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 av = __bfloat1622float2(a2[e]);
+        const float d0 = (act == 2) ? fmaf(-av.x, av.x, 1.0f) : (act == 1 ? (av.x > 0.0f ? 1.0f : 0.0f) : 1.0f);
+        const float d1 = (act == 2) ? fmaf(-av.y, av.y, 1.0f) : (act == 1 ? (av.y > 0.0f ? 1.0f : 0.0f) : 1.0f);
+        o2[e] = __floats2bfloat162_rn(gv[2 * e] * inv * d0, gv[2 * e + 1] * inv * d1);
+    }
+    const uint4 out = *reinterpret_cast<uint4*>(o2);
+    reinterpret_cast<uint4*>(dz + pix * C)[grp] = out;
+    if (w == 0) reinterpret_cast<uint4*>(dz + (pix + W) * C)[grp] = out;
+    if (w == W - 1) reinterpret_cast<uint4*>(dz + (pix - W) * C)[grp] = out;
 }
 
 // padded NHWC bf16 -> NCHW fp32 (interior only): the reference's feature-map layout, for checks / heads
@@ -961,8 +990,8 @@ extern "C" int delora_maxpool_w_bwd_nhwc_bf16(const void* dy, const void* idx, c
 
 extern "C" int delora_avgpool_bwd_nhwc_bf16(const float* g, const void* a, int B, int H, int W, int C, int act, void* dz,
                                             void* stream) {
-    DELORA_CHECK_ARG(g && a && dz, "delora_avgpool_bwd_nhwc_bf16: null pointer");
-    const size_t total = (size_t)B * H * W * C;
+    DELORA_CHECK_ARG(g && a && dz && C % 8 == 0, "delora_avgpool_bwd_nhwc_bf16: bad argument");
+    const size_t total = (size_t)B * H * W * (C / 8);
     avgpool_bwd_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         g, (const __nv_bfloat16*)a, B, H, W, C, act, (__nv_bfloat16*)dz);
     DELORA_CHECK_LAUNCH("avgpool_bwd_act_kernel");

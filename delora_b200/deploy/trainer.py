@@ -26,7 +26,9 @@ class Trainer(deployer.Deployer):
     def __init__(self, config):
         super().__init__(config=config)
         self.training_bool = True
-        self.optimizer = torch.optim.Adam(params=self.model.parameters(), lr=self.config["learning_rate"])
+        # the reference's optimizer (src/deploy/trainer.py:23-24); on CUDA torch's fused implementation of the same update
+        self.optimizer = torch.optim.Adam(params=self.model.parameters(), lr=self.config["learning_rate"],
+                                          fused=str(self.device).startswith("cuda"))
         if self.config.get("checkpoint"):
             checkpoint = torch.load(self.config["checkpoint"], map_location=self.device, weights_only=False)
             self.model.load_state_dict(checkpoint["model_state_dict"])

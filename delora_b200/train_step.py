@@ -36,7 +36,9 @@ class SyntheticTrainStep:
                     head[3].weight.zero_()
                     head[3].bias.copy_(torch.tensor(bias, device=self.device))
         self.autocast_bf16 = bool(autocast_bf16)       # torch / cuDNN path only: the reference stack under bf16 autocast
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr)
+        # same optimizer as the reference (src/deploy/trainer.py:23-24); on CUDA torch's fused implementation (one
+        # kernel for all parameters instead of ~7 multi-tensor launches, identical state_dict)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr, fused=self.device.type == "cuda")
         self.sync = make_grad_sync(self.model, grad_sync)
         self.scratch = ops.icp_scratch(self.B, self.H * self.W, self.device)
         self.points = torch.zeros((2 * self.B, 3, self.N), dtype=torch.float32, device=self.device)
