@@ -5,12 +5,15 @@
 // edge-clamped patch; :53-87 range gate, >= min neighbours, eigen-decomposition, orientation)
 // and utility.linalg.cov (src/utility/linalg.py:33-56 zero-aware mean / covariance).
 //
-// One CTA stages a (TH+2a) x (TW+2b) tile of (x, y, z, |p|) as float4 in shared memory (one
-// LDS.128 per tap), every thread owns one pixel: pass 1 = gated sum and count, pass 2 = centred
-// covariance (same two-pass arithmetic as the reference), then a cyclic Jacobi eigen-solve of the
-// 3x3 covariance in registers, smallest-eigenvalue eigenvector, flipped toward the sensor.
-// The kernel is FP32-issue / shared-memory bound (~2.4 kFLOP per pixel against 28 B of HBM
-// traffic), not HBM bound; see DESIGN.md.
+// One CTA stages a (TH+2a) x (TW+2b) tile of (x, y, z, |p|) as float4 in shared memory, already
+// edge-clamped (one LDS.128 per tap); every thread owns TWO vertically adjacent pixels as one packed
+// fp32x2 pair (FFMA2 / FADD2 / FMUL2).  ONE pass over the taps in coordinates relative to the pixel
+// itself: gated count, sum and second moments, then C = (sum w d d^T - n m m^T) / (n - 1) -- the
+// reference (linalg.py:33-56) subtracts the mean in a second sweep; shifting by the centre first makes
+// the one-pass form as accurate -- then a cyclic Jacobi eigen-solve of the 3x3
+// covariance in registers, smallest-eigenvalue eigenvector, flipped toward the sensor.
+// The kernel is FP32-pipe / issue bound (~2.4 kFLOP per pixel against 28 B of HBM traffic), not HBM
+// bound: bench.py reports it against the fp32 roofline; see DESIGN.md.
 #include "common.cuh"
 
 namespace delora {
