@@ -30,7 +30,8 @@
 
 namespace delora {
 
-constexpr int kRowsThreads = 224;
+constexpr int kRowsThreads = 224;                 // 3 role warps + 4 epilogue warps
+constexpr int kRowsThreadsPixm = 352;             // pixel-on-M form: 8 epilogue warps (two per TMEM lane quarter; 156 regs/thread)
 constexpr int kRowsMaxTaps = 9;
 constexpr int kRowsMaxPhases = 4;
 constexpr int kWTileBytes = 128 * 64 * 2;          // filter tile: 128 output channels x 64 input channels
@@ -85,7 +86,7 @@ __device__ __forceinline__ RowsJob rows_decode(const RowsParams& p, int job, int
 //         channels (B operand = filter tile [Cout / CG][64]); a thread of the epilogue owns a pixel, no transpose.
 //         With CG = 2 the pair covers 2 x 128 pixels and each CTA loads half of the filter rows.
 template <int CG, bool PIXM>
-__global__ void __launch_bounds__(kRowsThreads, 1)
+__global__ void __launch_bounds__(PIXM ? kRowsThreadsPixm : kRowsThreads, 1)
 conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __nv_bfloat16* __restrict__ residual, const __nv_bfloat16* __restrict__ saved,
                     __nv_bfloat16* __restrict__ y, const __grid_constant__ RowsParams p) {
@@ -111,7 +112,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1);
-            mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4 * CG);
+            mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, (PIXM ? 8 : 4) * CG);
         }
         for (int s = 0; s < S; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
         fence_barrier_init();
@@ -274,17 +275,18 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     bi.hr = wo == 0; bi.hl = wo == p.Wout - 1;
                     return bi;
                 };
-                Blk bn = info(0);
+                const int ehalf = (warp - 3) >> 2;                // 0 / 1: which of the quarter's two warps
+                Blk bn = info(ehalf < nb ? ehalf : 0);
                 EpiloguePrefetch nxt;
-                if (bn.in_range)
+                if (bn.in_range && ehalf < nb)
                     epilogue_prefetch32(nxt, bn.use_res ? residual + bn.roff : nullptr, saved + (p.act >= 3 ? bn.off : 0), 0, p.act);
                 mbar_wait(acc_full + ab, (j_it >> 1) & 1);
                 tc_fence_after();
-                for (int k = 0; k < nb; ++k) {
+                for (int k = ehalf; k < nb; k += 2) {             // the two warps of a lane quarter alternate blocks
                     const Blk bc = bn;
                     const EpiloguePrefetch cur = nxt;
-                    if (k + 1 < nb) {
-                        bn = info(k + 1);
+                    if (k + 2 < nb) {
+                        bn = info(k + 2);
                         if (bn.in_range)
                             epilogue_prefetch32(nxt, bn.use_res ? residual + bn.roff : nullptr, saved + (p.act >= 3 ? bn.off : 0), 0, p.act);
                     }
@@ -535,7 +537,8 @@ int conv_rows_launch(const void* x, const void* w, const void* residual, const v
     const int units = kNumSMs / cg;
     const int grid = (p.n_jobs < units ? p.n_jobs : units) * cg;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kRowsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(pixm ? kRowsThreadsPixm : kRowsThreads);
+    cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

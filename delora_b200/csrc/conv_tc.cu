@@ -811,11 +811,13 @@ extern "C" int delora_conv2d_fprop_bf16(const void* x, const void* w, const void
     const TensorMaps* maps = get_maps(x, w, B, Hin, Win, Cin, Cout, p);
     DELORA_CHECK_ARG(maps != nullptr, "delora_conv2d_fprop_bf16: cuTensorMapEncodeTiled failed or is unavailable");
     const size_t smem = (size_t)p.stages * (kBlockM * kBlockK * 2 + p.BN * kBlockK * 2) + (2 * kMaxStages + 1) * 8 + 16 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {};                       // the opt-in is per device (one process may drive several)
+    if (dev < 64 && !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         DELORA_CHECK_ARG(e == cudaSuccess, "delora_conv2d_fprop_bf16: smem opt-in failed: %s", cudaGetErrorString(e));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     dim3 grid(B * p.tiles_h * p.tiles_w, Cout / p.BN);
     conv_fprop_tc_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(
@@ -937,11 +939,13 @@ extern "C" int delora_conv2d_wgrad_bf16(const void* x, const void* dz, float* dw
         DELORA_CHECK_ARG(rc == CUDA_SUCCESS, "delora_conv2d_wgrad_bf16: tensor map (x) failed: %d", (int)rc);
     }
     const size_t smem = (size_t)p.stages * (2 + p.nb * p.tg) * 8192 + (2 * kMaxStages + 1) * 8 + 16 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {};
+    if (dev < 64 && !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         DELORA_CHECK_ARG(e == cudaSuccess, "delora_conv2d_wgrad_bf16: smem opt-in failed: %s", cudaGetErrorString(e));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(p.ksize * p.groups_per_row, co_tiles * p.ci_tiles, p.splits);

@@ -14,14 +14,24 @@ LOSS_ROW, ICP_PARTIAL = 8, 40
 _keys_cache = {}
 
 
+_last_device = [None]
+
+
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """The current stream of the device the operands live on (`_req` records it: with several devices in one process
+    torch's *current device* need not be the tensors' device) -- the kernels are launched on that device's stream."""
+    dev = _last_device[0]
+    return torch.cuda.current_stream(dev).cuda_stream
 
 
 def _req(t, dtype, name):
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
         raise ValueError(f"{name}: expected a contiguous CUDA tensor of dtype {dtype}, got "
                          f"{getattr(t, 'dtype', type(t))} on {getattr(t, 'device', '?')}")
+    if _last_device[0] != t.device:
+        _last_device[0] = t.device
+        if torch.cuda.current_device() != t.device.index:      # the C ABI launches on the CURRENT device
+            torch.cuda.set_device(t.device)
     return t.data_ptr()
 
 

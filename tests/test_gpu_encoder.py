@@ -176,3 +176,44 @@ def test_encoder_training_path_gradients(h, w, cuda_lib):
     t, q = model(image_1=img1, image_2=img2)
     (t.sum() + q.sum()).backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_flat_gradient_buffer_matches_plain_autograd(cuda_lib):
+    """parallel_grad.BucketedGradAllReduce on one process: the weight-gradient kernels write into the flat buffer,
+    `finish()` makes every p.grad a view of it -- same values as the plain autograd path, for two consecutive steps
+    and with a second forward before the first backward (separate buffer slots)."""
+    from delora_b200 import synthetic
+    from delora_b200.models.model import OdometryModel
+    from delora_b200.parallel_grad import BucketedGradAllReduce
+    h, w, b = 16, 256, 2
+    cfg = synthetic.fov_config(h=h, w=w, device=DEV)
+    cfg.update({"pre_feature_extraction": False, "resnet_outputs": 1000, "use_dropout": False, "layers": [2, 2, 2, 2],
+                "factor_fewer_resnet_channels": 1, "activation_fct": "tanh", "use_single_mlp_at_output": False})
+    torch.manual_seed(0)
+    model = OdometryModel(cfg).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    img = [torch.randn(b, 4, h, w, device=DEV, generator=g) * 5.0 for _ in range(4)]
+
+    def loss_of(i1, i2):
+        t, q = model(image_1=i1, image_2=i2)
+        return (t * 0.7).sum() + (q * 1.3).sum()
+    model.zero_grad(set_to_none=True)
+    loss_of(img[0], img[1]).backward()
+    ref = [p.grad.clone() for p in model.parameters()]
+    sync = BucketedGradAllReduce(model, encoder=model._tensor_core_path())
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        loss_of(img[0], img[1]).backward()
+        sync.finish()
+        for p, r in zip(model.parameters(), ref):
+            assert p.grad.data_ptr() == sync.views[id(p)].data_ptr()
+            assert torch.equal(p.grad, r)
+    # two forwards alive at once: the second must not clobber the activations the first backward needs
+    model.zero_grad(set_to_none=True)
+    l1 = loss_of(img[0], img[1])
+    l2 = loss_of(img[2], img[3])
+    l1.backward()
+    sync.finish()
+    for p, r in zip(model.parameters(), ref):
+        assert torch.equal(p.grad, r)
+    del l2
