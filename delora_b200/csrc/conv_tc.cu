@@ -621,6 +621,93 @@ maxpool_bwd_act_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __re
     if (w == W - 1) reinterpret_cast<uint4*>(dz + (pix - W) * C)[grp] = out;
 }
 
+// Tiled form of maxpool_bwd_act_kernel for C = 64, W % 32 == 0 (the stem's shape): a CTA owns 4 input rows x 32 input
+// columns; the argmax bytes and dy rows of the (6 x 17 [+ the wrap window]) pooling windows that touch the tile are
+// staged ONCE in shared memory (coalesced 8- / 16-byte loads), then every (pixel, 8-channel group) gathers its <= 9
+// candidate windows from there in the same fixed order as the per-pixel kernel (bit-identical results, no atomics).
+// The per-pixel kernel re-read each argmax word from L1/L2 nine times (283 us at B = 16, 64 x 1024 x 64).
+constexpr int kPoolTH = 4, kPoolTW = 32;
+__global__ void __launch_bounds__(256)
+maxpool_bwd_tile_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                        const __nv_bfloat16* __restrict__ a, int B, int H, int W, int act,
+                        __nv_bfloat16* __restrict__ dz, int a_f16) {
+    constexpr int C = 64, G = 8, NR = kPoolTH + 2, NC = kPoolTW / 2 + 2;       // 6 window rows, 17 columns + wrap slot
+    __shared__ uint2 s_idx[NR][NC][G];
+    __shared__ uint4 s_dy[NR][NC][G];
+    const int Wout = W / 2, Wp = W + 2, Hp = H + 2, Wpo = Wout + 2;
+    const int w0 = blockIdx.x * kPoolTW, h0 = blockIdx.y * kPoolTH, b = blockIdx.z;
+    const bool last_tile = (w0 + kPoolTW == W);
+    for (int t = threadIdx.x; t < NR * NC * G; t += 256) {
+        const int grp = t % G, wi = (t / G) % NC, ri = t / (G * NC);
+        const int ho = h0 - 1 + ri;
+        const int wo = (wi < NC - 1) ? (w0 >> 1) + wi : 0;                     // slot NC-1: the window at wo = 0 (circular halo)
+        const bool valid = ho >= 0 && ho < H && wo < Wout && (wi < NC - 1 || last_tile);
+        s_idx[ri][wi][grp] = valid ? __ldg(reinterpret_cast<const uint2*>(idx + (((size_t)b * H + ho) * Wout + wo) * C) + grp)
+                                   : make_uint2(0xffffffffu, 0xffffffffu);
+        s_dy[ri][wi][grp] = valid ? __ldg(reinterpret_cast<const uint4*>(dy + (((size_t)b * Hp + ho + 1) * Wpo + wo + 1) * C) + grp)
+                                  : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < kPoolTH * kPoolTW * G; item += 256) {
+        const int grp = item % G, lw = (item / G) % kPoolTW, lh = item / (G * kPoolTW);
+        const int h = h0 + lh, w = w0 + lw;
+        if (h >= H) continue;
+        float g[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = 0.0f;
+        // candidate windows in the per-pixel kernel's order: (wo, dq) from padded column wp = w + 1, then the halo copy
+        const int wp = w + 1, odd = wp & 1;
+        const int c_wi[3] = {(odd ? (wp - 1) >> 1 : wp >> 1) - (w0 >> 1), (wp >> 1) - 1 - (w0 >> 1), NC - 1};
+        const int c_dq[3] = {odd ? 1 : 0, 2, 0};
+        const bool c_ok[3] = {true, !odd, w == W - 1};
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+            if (!c_ok[ci]) continue;
+#pragma unroll
+            for (int dr = 0; dr < 3; ++dr) {
+                const int ri = lh - dr + 2;                                    // window row ho = h - dr + 1
+                const uint2 am = s_idx[ri][c_wi[ci]][grp];
+                const unsigned want = (unsigned)(dr * 3 + c_dq[ci]) * 0x01010101u;
+                const unsigned eq_lo = am.x ^ want, eq_hi = am.y ^ want;       // zero byte = this window's argmax is (h, w)
+                if ((((eq_lo - 0x01010101u) & ~eq_lo) | ((eq_hi - 0x01010101u) & ~eq_hi)) & 0x80808080u) {
+                    const uint4 raw = s_dy[ri][c_wi[ci]][grp];
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(h2[e]);
+                        const unsigned word = (e < 2) ? eq_lo : eq_hi;
+                        if (((word >> (16 * (e & 1))) & 0xffu) == 0u) g[2 * e] += f.x;
+                        if (((word >> (16 * (e & 1) + 8)) & 0xffu) == 0u) g[2 * e + 1] += f.y;
+                    }
+                }
+            }
+        }
+        const uint4 araw = __ldg(reinterpret_cast<const uint4*>(a + (((size_t)b * Hp + h + 1) * Wp + w + 1) * C) + grp);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&araw);
+        const __half2* a2h = reinterpret_cast<const __half2*>(&araw);
+        __nv_bfloat162 o2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 av = a_f16 ? __half22float2(a2h[e]) : __bfloat1622float2(a2[e]);
+            float d0, d1;
+            if (act == 6) {
+                const float e0 = __expf(-2.0f * fabsf(av.x)), e1 = __expf(-2.0f * fabsf(av.y));
+                d0 = __fdividef(4.0f * e0, (1.0f + e0) * (1.0f + e0));
+                d1 = __fdividef(4.0f * e1, (1.0f + e1) * (1.0f + e1));
+            } else {
+                d0 = (act == 2) ? fmaf(-av.x, av.x, 1.0f) : ((act == 1 || act == 5) ? (av.x > 0.0f ? 1.0f : 0.0f) : 1.0f);
+                d1 = (act == 2) ? fmaf(-av.y, av.y, 1.0f) : ((act == 1 || act == 5) ? (av.y > 0.0f ? 1.0f : 0.0f) : 1.0f);
+            }
+            o2[e] = __floats2bfloat162_rn(g[2 * e] * d0, g[2 * e + 1] * d1);
+        }
+        const uint4 out = *reinterpret_cast<uint4*>(o2);
+        const size_t pix = ((size_t)b * Hp + h + 1) * Wp + w + 1;
+        reinterpret_cast<uint4*>(dz + pix * C)[grp] = out;
+        if (w == 0) reinterpret_cast<uint4*>(dz + (pix + W) * C)[grp] = out;
+        if (w == W - 1) reinterpret_cast<uint4*>(dz + (pix - W) * C)[grp] = out;
+    }
+}
+
 // Backward of AdaptiveAvgPool2d((1,1)) fused with the derivative of the last block's activation:
 // dz[b,h,w,c] = g[b,c] / (H*W) * act'(a[b,h,w,c]), padded NHWC with halo.
 __global__ void __launch_bounds__(256)
@@ -984,6 +1071,14 @@ extern "C" int delora_maxpool_w_idx_nhwc_bf16(const void* x, int B, int H, int W
 extern "C" int delora_maxpool_w_bwd_nhwc_bf16(const void* dy, const void* idx, const void* a, int B, int H, int W, int C,
                                               int act, void* dz, int a_f16, void* stream) {
     DELORA_CHECK_ARG(dy && idx && a && dz && W % 2 == 0 && C % 8 == 0, "delora_maxpool_w_bwd_nhwc_bf16: bad argument");
+    if (C == 64 && W % kPoolTW == 0 && B <= 65535) {
+        dim3 grid((unsigned)(W / kPoolTW), (unsigned)((H + kPoolTH - 1) / kPoolTH), (unsigned)B);
+        maxpool_bwd_tile_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)dy, (const uint8_t*)idx, (const __nv_bfloat16*)a, B, H, W, act, (__nv_bfloat16*)dz,
+            a_f16 ? 1 : 0);
+        DELORA_CHECK_LAUNCH("maxpool_bwd_tile_kernel");
+        return 0;
+    }
     const size_t total = (size_t)B * H * W * (C / 8);
     maxpool_bwd_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dy, (const uint8_t*)idx, (const __nv_bfloat16*)a, B, H, W, C, act, (__nv_bfloat16*)dz,

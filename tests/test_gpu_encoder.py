@@ -217,3 +217,54 @@ def test_flat_gradient_buffer_matches_plain_autograd(cuda_lib):
     for p, r in zip(model.parameters(), ref):
         assert torch.equal(p.grad, r)
     del l2
+
+
+@pytest.mark.parametrize("h,w,f16,act", [(5, 64, True, 2), (9, 96, False, 1), (4, 1024, True, 2), (5, 48, True, 2),
+                                          (3, 90, False, 2)])
+def test_maxpool_forward_argmax_and_backward(h, w, f16, act, cuda_lib):
+    """The stem's max pool (3x3, stride (1, 2), circular in W, activation applied to the maximum) and its backward
+    (tiled kernel for W % 32 == 0, per-pixel kernel otherwise): pooled values against torch's max_pool2d, the stored
+    argmax against the input, and dz against a scatter-add of dy through those argmax codes times act'(z)."""
+    from delora_b200 import ops
+    L = ops._lib.lib()
+    b, c, wo = 2, 64, w // 2
+    g = torch.Generator(device=DEV).manual_seed(h * 1000 + w)
+    z = (torch.randn((b, c, h, w), generator=g, device=DEV) * 1.5)
+    z = z.to(torch.float16 if f16 else torch.bfloat16)
+    zp = F.pad(F.pad(z.float(), (1, 1, 0, 0), mode="circular"), (0, 0, 1, 1))           # halo as the conv epilogue leaves it
+    y0 = zp.permute(0, 2, 3, 1).contiguous().to(z.dtype)
+    pooled = ops.padded_nhwc_zeros(b, h, wo, c, DEV)
+    idx = torch.empty((b, h, wo, c), dtype=torch.uint8, device=DEV)
+    ops._lib.check(L.delora_maxpool_w_idx_nhwc_bf16(y0.data_ptr(), b, h, w, c, pooled.data_ptr(), idx.data_ptr(), act,
+                                                    1 if f16 else 0, ops._stream()), "maxpool idx")
+    f = torch.tanh if act == 2 else torch.relu
+    zinf = F.pad(F.pad(z.float(), (1, 1, 0, 0), mode="circular"), (0, 0, 1, 1), value=float("-inf"))
+    ref = F.max_pool2d(zinf, 3, stride=(1, 2))[..., :wo]
+    got = pooled[:, 1:h + 1, 1:wo + 1].permute(0, 3, 1, 2).float()
+    assert torch.allclose(got, f(ref), rtol=2 ** -7, atol=0)          # bf16 rounding of the device tanh: <= 1 ulp
+    # the argmax code dr * 3 + dq points at an element equal to the window maximum
+    code = idx.permute(0, 3, 1, 2).long()
+    assert int(code.max()) <= 8
+    win = zinf.unfold(2, 3, 1).unfold(3, 3, 2)[:, :, :, :wo].reshape(b, c, h, wo, 9)
+    assert torch.equal(win.gather(4, code.unsqueeze(-1)).squeeze(-1), ref)
+
+    dy = torch.randn((b, h, wo, c), generator=g, device=DEV).to(torch.bfloat16)
+    dyp = ops.padded_nhwc_zeros(b, h, wo, c, DEV)
+    dyp[:, 1:h + 1, 1:wo + 1] = dy
+    dyp[:, :, 0] = dyp[:, :, wo]
+    dyp[:, :, wo + 1] = dyp[:, :, 1]
+    dz = torch.full((b, h + 2, w + 2, c), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops._lib.check(L.delora_maxpool_w_bwd_nhwc_bf16(dyp.data_ptr(), idx.data_ptr(), y0.data_ptr(), b, h, w, c, 4 + act,
+                                                    dz.data_ptr(), 1 if f16 else 0, ops._stream()), "maxpool bwd")
+    acc = torch.zeros((b, h + 2, w + 2, c), dtype=torch.float32, device=DEV)
+    for dr in range(3):
+        for dq in range(3):
+            acc[:, dr:dr + h, dq:dq + 2 * wo:2] += dy.float() * (idx == dr * 3 + dq)
+    acc[:, :, w] += acc[:, :, 0]
+    acc[:, :, 1] += acc[:, :, w + 1]
+    zf = z.float().permute(0, 2, 3, 1)
+    dact = (1.0 - torch.tanh(zf) ** 2) if act == 2 else (zf > 0).float()
+    want = acc[:, 1:h + 1, 1:w + 1] * dact
+    out = dz[:, 1:h + 1, 1:w + 1].float()
+    assert torch.allclose(out, want, rtol=2 ** -7, atol=1e-6)
+    assert torch.equal(dz[:, 1:h + 1, 0], dz[:, 1:h + 1, w]) and torch.equal(dz[:, 1:h + 1, w + 1], dz[:, 1:h + 1, 1])
