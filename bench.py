@@ -249,12 +249,20 @@ def train_leg(args, rank, world, device, raw, n_max):
 
     ts = build(use_tensor_cores=True, grad_sync="bucketed")
     ms, loss = timed(ts, args.train_steps)
+    transport = getattr(ts.sync, "transport", "none") if world > 1 else "none"
+    transport_note = getattr(ts.sync, "transport_note", "")
+    if world > 1 and getattr(ts.sync, "peer", None) is not None:
+        ts.sync.peer.check()            # raises if some rank missed a collective
     out = {"ms_per_step": ms, "pairs_per_s": world * tb / (ms * 1e-3), "n_gpus": world, "batch_per_gpu": tb,
            "loss": loss, "encoder_gflop_per_step": 3 * 96.17 * tb,
            "workload": f"full training step, batch {tb}/GPU, 64x{W}: projection + normals + tcgen05 encoder fwd/bwd "
                        "(bf16) + heads + fused ICP loss fwd/bwd (fp32) + Adam"
-                       + (" + bucketed NCCL all-reduce of 11.88 M fp32 gradients overlapped with the backward"
-                          if world > 1 else "")}
+                       + (" + per-bucket all-reduce of 11.88 M fp32 gradients overlapped with the backward (transport: "
+                          + transport + ")" if world > 1 else "")}
+    if world > 1:
+        out["allreduce_transport"] = transport
+        if transport_note:
+            out["allreduce_transport_note"] = transport_note
     if world == 1:
         # encoder alone: forward + backward of the trunk on fixed images -> achieved bf16 TFLOP/s vs the measured peak
         enc = ts.model._tensor_core_path()
@@ -289,6 +297,11 @@ def train_leg(args, rank, world, device, raw, n_max):
         del ts
         out.update({"ms_without_allreduce": ms_none, "allreduce_exposed_ms": ms - ms_none,
                     "ms_blocking_flat_allreduce": ms_flat})
+        if transport != "nccl":
+            ts = build(use_tensor_cores=True, grad_sync="bucketed-nccl")
+            ms_nccl, _ = timed(ts, args.train_steps)
+            del ts
+            out.update({"ms_bucketed_nccl": ms_nccl, "allreduce_exposed_ms_nccl": ms_nccl - ms_none})
     elif rank == 0 and args.cudnn_steps > 0:
         ts = build(use_tensor_cores=False)
         out["cudnn_fp32_ms"], _ = timed(ts, args.cudnn_steps)

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdelora_b200.so")
-SOURCES = ["api.cu", "projection.cu", "normals.cu", "lists.cu", "icp.cu", "icp_dense.cu", "sort.cu", "conv_tc.cu", "conv_rows.cu", "conv_wgrad.cu", "conv_stem.cu"]
+SOURCES = ["api.cu", "projection.cu", "normals.cu", "lists.cu", "icp.cu", "icp_dense.cu", "sort.cu", "conv_tc.cu", "conv_rows.cu", "conv_wgrad.cu", "conv_stem.cu", "grad_allreduce.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas=-v"]
 

@@ -35,6 +35,10 @@ constexpr int kRowsThreadsPixm = 352;             // pixel-on-M form: 8 epilogue
 constexpr int kRowsMaxTaps = 9;
 constexpr int kRowsMaxPhases = 4;
 constexpr int kWTileBytes = 128 * 64 * 2;          // filter tile: 128 output channels x 64 input channels
+// Dynamic shared memory of one persistent CTA: 226 KB, not the 227 KB maximum -- 228 KB per SM minus this and the 1 KB
+// the system reserves per CTA leaves room for ONE more (shared-memory-free) CTA on the SM, which is what lets the
+// gradient all-reduce kernel (grad_allreduce.cu) run beside the convolutions instead of between them.
+constexpr int kRowsSmemBudget = 226 * 1024;
 
 struct RowsPhase {
     int ntaps;
@@ -512,7 +516,7 @@ int conv_rows_launch(const void* x, const void* w, const void* residual, const v
     p.n_jobs = p.n_phases * B * p.blocks_h * p.segs_w * p.co_tiles;
     p.a_stage_bytes = (((p.NS + 2) * (p.R + 2) * 128) + 1023) / 1024 * 1024;
     const int fixed = 2 * p.a_stage_bytes + 4 * 4096 + 256 + 1024;
-    int ws = (227 * 1024 - fixed) / p.w_tile_bytes;
+    int ws = (kRowsSmemBudget - fixed) / p.w_tile_bytes;
     if (ws > 8) ws = 8;
     DELORA_CHECK_ARG(ws >= 2, "conv_rows: tile %dx%d leaves no room for the filter ring", p.NS, p.R);
     p.w_stages = ws;

@@ -6,9 +6,19 @@ only collective of the training step.  One process per GPU, launched with torchr
 `BucketedGradAllReduce` (the training path): every gradient is a view of ONE persistent flat fp32 buffer (11.88 M
 elements = 47.5 MB for the default model) laid out in BACKWARD order as a few buckets (heads + fc | layer4 | layer3 |
 layer2 | layer1 + stem).  The tensor-core encoder writes its weight gradients straight into the flat slices (no copies)
-and announces each group from inside its backward, so NCCL reduces layer4 (33.6 MB) on its own stream while the
-backward of layers 3 -> 1 still runs; only the last small bucket is exposed.  `FlatGradAllReduce` (one blocking
-all-reduce after backward) is kept for the CPU / gloo tests and as the measured baseline of the overlap."""
+and announces each group from inside its backward, so layer4 (33.6 MB) is reduced while the backward of layers 3 -> 1
+still runs; only the last small bucket is exposed.
+
+Transport of a bucket (`transport=`):
+  "peer"  the flat buffer is symmetric memory (mapped at every peer of the node, NVSwitch multicast where available)
+          and `delora_grad_allreduce_f32` (csrc/grad_allreduce.cu) reduces it in place over NVLink: a 128-thread,
+          shared-memory-free kernel whose CTAs are resident NEXT TO the persistent tcgen05 convolution CTAs.  NCCL's
+          CTAs cannot share an SM with those, which left 0.25 ms of the collective exposed per step at 8 GPUs.
+  "nccl"  `dist.all_reduce(AVG, async_op=True)` per bucket (any backend; gloo on CPU uses SUM + divide).
+  "auto"  "peer" on CUDA when the symmetric-memory rendezvous succeeds on EVERY rank, else "nccl".
+`FlatGradAllReduce` (one blocking all-reduce after backward) is kept for the CPU / gloo tests and as the measured
+baseline of the overlap."""
+import ctypes
 
 import torch
 import torch.distributed as dist
@@ -59,6 +69,65 @@ class FlatGradAllReduce:
     finish = all_reduce
 
 
+class _PeerTransport:
+    """Symmetric flat buffer + flag words + the launch of csrc/grad_allreduce.cu.  torch supplies the plumbing only
+    (CUDA VMM allocation, handle exchange over the process group's store, the multicast binding)."""
+
+    BUCKET_ALIGN = 128          # floats: buckets start on 512-byte boundaries (16-byte vectors, whole sectors)
+
+    def __init__(self, total, device, group, n_ctas=16):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib = _lib
+        L = _lib.lib()
+        pg = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(pg), dist.get_rank(pg)
+        self.flat = symm_mem.empty(total, dtype=torch.float32, device=device)
+        self.flat.zero_()
+        self.flags = symm_mem.empty(L.delora_grad_allreduce_flag_words(), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        hb = symm_mem.rendezvous(self.flat, pg.group_name)
+        hf = symm_mem.rendezvous(self.flags, pg.group_name)
+        self._handles = (hb, hf)
+        u64 = ctypes.c_uint64 * self.world
+        self.peer_bufs = u64(*[int(x) for x in hb.buffer_ptrs])
+        self.peer_flags = u64(*[int(x) for x in hf.buffer_ptrs])
+        self.multicast = int(hb.multicast_ptr or 0)
+        self.n_ctas = int(n_ctas)
+        self.seq = 0
+        # the collective's own stream: it waits for the bucket's producers, then runs beside the rest of the backward
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
+        self._done = None           # (the rendezvous above is the barrier "every rank has zeroed its flags")
+
+    def launch(self, start, end):
+        cur = torch.cuda.current_stream(self.flat.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.stream.wait_event(ready)
+        self.seq += 1
+        L = self._lib.lib()
+        self._lib.check(L.delora_grad_allreduce_f32(self.peer_bufs, self.peer_flags, self.multicast, self.rank, self.world,
+                                                    start, end - start, 1.0 / self.world, self.seq & 0x7fffffff,
+                                                    self.n_ctas, self.status.data_ptr(), self.stream.cuda_stream),
+                        "delora_grad_allreduce_f32")
+        self._done = torch.cuda.Event()
+        self._done.record(self.stream)
+
+    def wait(self):
+        if self._done is not None:
+            torch.cuda.current_stream(self.flat.device).wait_event(self._done)
+            self._done = None
+
+    def check(self):
+        """Host-synchronising: raises if a peer failed to arrive in some collective since the last check."""
+        code = int(self.status.item())
+        if code:
+            self.status.zero_()
+            raise RuntimeError(f"delora_grad_allreduce_f32: rank {code - 1} did not arrive within the time limit")
+
+
 class BucketedGradAllReduce:
     """Flat gradient buffer + bucketed, overlapped all-reduce.  Usage per step:
         optimizer.zero_grad(set_to_none=True); loss.backward(); sync.finish(); optimizer.step()
@@ -66,10 +135,12 @@ class BucketedGradAllReduce:
     view of the flat buffer that holds the averaged gradient.  With WORLD_SIZE == 1 the buffer and the direct
     gradient writes are still used (no copies), only the collectives are skipped."""
 
-    def __init__(self, module, encoder=None, process_group=None, enabled=True):
+    def __init__(self, module, encoder=None, process_group=None, enabled=True, transport="auto"):
         self.world, self.rank = _world(process_group)
         self.group = process_group
         self.enabled = bool(enabled)
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError(f"transport must be auto, peer or nccl, got {transport!r}")
         params = [p for p in module.parameters() if p.requires_grad]
         trunk = list(encoder.trunk_parameters()) if encoder is not None else []
         trunk_ids = {id(p) for p in trunk}
@@ -86,8 +157,24 @@ class BucketedGradAllReduce:
                     self._trunk_bucket[i] = bi + 1
         self.buckets = [b for b in buckets]
         device = params[0].device
-        total = sum(p.numel() for p in params)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        align = _PeerTransport.BUCKET_ALIGN
+        total = sum((sum(p.numel() for p in b) + align - 1) // align * align for b in self.buckets)
+        self.peer, self.transport, self.transport_note = None, "nccl", ""
+        if self.world > 1 and self.enabled and transport != "nccl" and device.type == "cuda":
+            ok = 1
+            try:
+                self.peer = _PeerTransport(total, device, process_group)
+            except Exception as e:                       # no VMM / fabric handle support, rendezvous refused, ...
+                ok, self.peer, self.transport_note = 0, None, f"{type(e).__name__}: {e}"[:300]
+            agree = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)
+            if int(agree.item()) == 0:
+                if transport == "peer":
+                    raise RuntimeError("peer-memory gradient transport unavailable on some rank: " + self.transport_note)
+                self.peer = None
+            else:
+                self.transport = "peer-multicast" if self.peer.multicast else "peer"
+        self.flat = self.peer.flat if self.peer is not None else torch.zeros(total, dtype=torch.float32, device=device)
         self.views, self.ranges, self._bucket_of = {}, [], {}
         off = 0
         for bi, b in enumerate(self.buckets):
@@ -97,6 +184,7 @@ class BucketedGradAllReduce:
                 self.views[id(p)] = self.flat[off:off + n].view_as(p)
                 self._bucket_of[id(p)] = bi
                 off += n
+            off = (off + align - 1) // align * align       # padding stays zero: reduced along, never read
             self.ranges.append((start, off))
         self.params = params
         self._pending = [0] * len(self.buckets)
@@ -141,6 +229,9 @@ class BucketedGradAllReduce:
         s, e = self.ranges[bi]
         if e == s:
             return
+        if self.peer is not None:
+            self.peer.launch(s, e)
+            return
         chunk = self.flat[s:e]
         if dist.get_backend(self.group) == "nccl":
             self._works.append((dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True), None))
@@ -173,6 +264,8 @@ class BucketedGradAllReduce:
             work.wait()
             if chunk is not None:
                 chunk.div_(self.world)
+        if self.peer is not None:
+            self.peer.wait()
         for p in self.params:
             view = self.views[id(p)]
             if p.grad is None or p.grad.data_ptr() != view.data_ptr():
@@ -183,14 +276,16 @@ class BucketedGradAllReduce:
 
 
 def make_grad_sync(model, mode="bucketed", process_group=None):
-    """The gradient synchroniser of a training loop: "bucketed" (flat buffer, overlapped per-bucket all-reduce; also
-    used on one GPU with the tensor-core encoder, where it only removes gradient copies), "flat" (one blocking
-    all-reduce after backward), "none" (no collective: the measured reference for the exposed all-reduce time)."""
+    """The gradient synchroniser of a training loop: "bucketed" (flat buffer, overlapped per-bucket all-reduce over peer
+    memory when available, else NCCL; also used on one GPU with the tensor-core encoder, where it only removes gradient
+    copies), "bucketed-nccl" (the same with NCCL forced: the measured baseline of the peer-memory kernel), "flat" (one
+    blocking all-reduce after backward), "none" (no collective: the measured reference for the exposed all-reduce time)."""
     encoder = model._tensor_core_path() if hasattr(model, "_tensor_core_path") else None
     world, _ = _world(process_group)
     if mode == "flat" or (encoder is None and world == 1):
         return FlatGradAllReduce(model, process_group)
-    return BucketedGradAllReduce(model, encoder=encoder, process_group=process_group, enabled=(mode != "none"))
+    return BucketedGradAllReduce(model, encoder=encoder, process_group=process_group, enabled=(mode != "none"),
+                                 transport="nccl" if mode == "bucketed-nccl" else "auto")
 
 
 def shard_pairs(num_pairs, rank, world):

@@ -332,6 +332,25 @@ int delora_quat_to_T(const float* quaternion, const float* translation, int B, f
 int delora_quat_to_T_bwd(const float* quaternion, const float* grad_T, int B,
                          float* grad_quaternion, float* grad_translation, void* stream);
 
+/* ---- Data-parallel training step: average of the weight gradients over the ranks (the reference
+ * steps one optimizer on one device, src/deploy/trainer.py:23-24, on `loss / batch_size`, src/deploy/deployer.py:329-342
+ * -- equal per-rank batches + the mean over ranks reproduce it over the global batch).
+ * One all-reduce of elements [offset, offset + count) of a flat fp32 buffer that is SYMMETRIC memory: allocated with
+ * the same size on every rank of the node and mapped into every peer (CUDA VMM / torch symmetric memory).
+ * peer_bufs[q] / peer_flags[q]: HOST arrays of `world` device addresses -- where rank q's flat buffer / flag words are
+ *   mapped in THIS process (index `rank` = the local ones).  Flag words: delora_grad_allreduce_flag_words() uint32,
+ *   zeroed once before the first call.
+ * multicast_ptr: address of the flat buffer's NVSwitch multicast mapping, or 0 (then peers are read / written one by
+ *   one in rank order).  seq: a counter that increases by one with every call, identical on all ranks.
+ * scale: applied to the sum (1 / world for the average).  status: device int32, set non-zero if a peer did not arrive
+ *   within 20 s (the kernel then carries on; it never hangs).  The kernel needs no shared memory and few registers so
+ *   that its n_ctas CTAs are resident NEXT TO the persistent convolution CTAs and the reduction overlaps the backward.
+ * Every rank must call it with the same offset / count / seq / n_ctas. */
+int delora_grad_allreduce_flag_words(void);
+int delora_grad_allreduce_f32(const uint64_t* peer_bufs, const uint64_t* peer_flags, uint64_t multicast_ptr, int rank,
+                              int world, long long offset, long long count, float scale, uint32_t seq, int n_ctas,
+                              int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
