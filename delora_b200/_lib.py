@@ -70,7 +70,7 @@ SIGNATURES = {
     "delora_quat_to_T_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "delora_grad_allreduce_flag_words": (c_int, []),
     "delora_grad_allreduce_f32": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, c_int, c_int, ctypes.c_longlong,
-                                          ctypes.c_longlong, c_float, c_u32, c_int, c_void_p, c_void_p]),
+                                          ctypes.c_longlong, c_float, c_u32, c_int, c_int, c_void_p, c_void_p]),
 }
 
 ABI_VERSION = 1

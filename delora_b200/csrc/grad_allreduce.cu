@@ -27,9 +27,9 @@
 
 namespace delora {
 
-constexpr int kArThreads = 128;
+constexpr int kArMaxThreads = 128;
 constexpr int kArMaxWorld = 16;
-constexpr int kArMaxCtas = 64;
+constexpr int kArMaxCtas = 160;
 constexpr unsigned long long kArTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 struct ArParams {
@@ -99,7 +99,7 @@ __device__ __forceinline__ void ar_meet(const ArParams& p, int phase, int cta) {
 }
 
 template <bool MC>
-__global__ void __launch_bounds__(kArThreads)
+__global__ void __launch_bounds__(kArMaxThreads)
 grad_allreduce_kernel(ArParams p) {
     const int cta = blockIdx.x;
     ar_meet(p, 0, cta);                                             // every rank's bucket is complete
@@ -110,12 +110,13 @@ grad_allreduce_kernel(ArParams p) {
     const long long hi_raw = (p.off >> 2) + ((long long)(p.rank + 1) * per < n4 ? (long long)(p.rank + 1) * per : n4);
     const long long hi = hi_raw > lo ? hi_raw : lo;
     constexpr int U = 4;                                            // independent 16-byte requests in flight per thread
-    const long long step = (long long)gridDim.x * kArThreads * U;
-    for (long long i0 = lo + (long long)cta * kArThreads * U + threadIdx.x; i0 < hi; i0 += step) {
+    const int nt = blockDim.x;
+    const long long step = (long long)gridDim.x * nt * U;
+    for (long long i0 = lo + (long long)cta * nt * U + threadIdx.x; i0 < hi; i0 += step) {
         float4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long i = i0 + (long long)u * kArThreads;
+            const long long i = i0 + (long long)u * nt;
             if (i < hi) {
                 if (MC) {
                     v[u] = multimem_ld_reduce_add(reinterpret_cast<const float4*>(p.mc) + i);
@@ -131,7 +132,7 @@ grad_allreduce_kernel(ArParams p) {
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long i = i0 + (long long)u * kArThreads;
+            const long long i = i0 + (long long)u * nt;
             if (i < hi) {
                 const float4 o = make_float4(v[u].x * p.scale, v[u].y * p.scale, v[u].z * p.scale, v[u].w * p.scale);
                 if (MC) {
@@ -155,7 +156,7 @@ extern "C" int delora_grad_allreduce_flag_words(void) { return 2 * kArMaxCtas * 
 
 extern "C" int delora_grad_allreduce_f32(const uint64_t* peer_bufs, const uint64_t* peer_flags, uint64_t multicast_ptr,
                                          int rank, int world, long long offset, long long count, float scale,
-                                         uint32_t seq, int n_ctas, int32_t* status, void* stream) {
+                                         uint32_t seq, int n_ctas, int n_threads, int32_t* status, void* stream) {
     DELORA_CHECK_ARG(peer_bufs && peer_flags && status, "delora_grad_allreduce_f32: null pointer");
     DELORA_CHECK_ARG(world >= 1 && world <= kArMaxWorld && rank >= 0 && rank < world,
                      "delora_grad_allreduce_f32: bad rank %d / world %d (max %d)", rank, world, kArMaxWorld);
@@ -163,6 +164,8 @@ extern "C" int delora_grad_allreduce_f32(const uint64_t* peer_bufs, const uint64
                      "delora_grad_allreduce_f32: offset %lld / count %lld must be multiples of 4 floats", offset, count);
     DELORA_CHECK_ARG(n_ctas >= 1 && n_ctas <= kArMaxCtas, "delora_grad_allreduce_f32: n_ctas %d outside [1, %d]", n_ctas,
                      kArMaxCtas);
+    DELORA_CHECK_ARG(n_threads >= 32 && n_threads <= kArMaxThreads && n_threads % 32 == 0,
+                     "delora_grad_allreduce_f32: n_threads %d must be 32, 64, 96 or 128", n_threads);
     if (count == 0) return 0;
     ArParams p;
     for (int q = 0; q < kArMaxWorld; ++q) {
@@ -176,9 +179,9 @@ extern "C" int delora_grad_allreduce_f32(const uint64_t* peer_bufs, const uint64
     p.rank = rank; p.world = world; p.off = offset; p.count = count; p.scale = scale; p.seq = seq; p.status = status;
     cudaStream_t st = (cudaStream_t)stream;
     if (p.mc)
-        grad_allreduce_kernel<true><<<n_ctas, kArThreads, 0, st>>>(p);
+        grad_allreduce_kernel<true><<<n_ctas, n_threads, 0, st>>>(p);
     else
-        grad_allreduce_kernel<false><<<n_ctas, kArThreads, 0, st>>>(p);
+        grad_allreduce_kernel<false><<<n_ctas, n_threads, 0, st>>>(p);
     DELORA_CHECK_LAUNCH("grad_allreduce_kernel");
     return 0;
 }

@@ -19,6 +19,7 @@ Transport of a bucket (`transport=`):
 `FlatGradAllReduce` (one blocking all-reduce after backward) is kept for the CPU / gloo tests and as the measured
 baseline of the overlap."""
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -75,7 +76,7 @@ class _PeerTransport:
 
     BUCKET_ALIGN = 128          # floats: buckets start on 512-byte boundaries (16-byte vectors, whole sectors)
 
-    def __init__(self, total, device, group, n_ctas=16):
+    def __init__(self, total, device, group, n_ctas=16, n_threads=128):
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self._lib = _lib
@@ -95,25 +96,35 @@ class _PeerTransport:
         self.peer_bufs = u64(*[int(x) for x in hb.buffer_ptrs])
         self.peer_flags = u64(*[int(x) for x in hf.buffer_ptrs])
         self.multicast = int(hb.multicast_ptr or 0)
-        self.n_ctas = int(n_ctas)
+        self.n_ctas = int(os.environ.get("DELORA_AR_CTAS", n_ctas))
+        self.n_threads = int(os.environ.get("DELORA_AR_THREADS", n_threads))
+        self.noop = os.environ.get("DELORA_AR_NOOP") == "1"        # experiments: everything but the kernel
         self.seq = 0
         # the collective's own stream: it waits for the bucket's producers, then runs beside the rest of the backward
         self.stream = torch.cuda.Stream(device=device, priority=-1)
         self._done = None           # (the rendezvous above is the barrier "every rank has zeroed its flags")
+        self.trace = None           # set to [] to collect (start, end, t_start_event, t_end_event) per launch
 
     def launch(self, start, end):
         cur = torch.cuda.current_stream(self.flat.device)
-        ready = torch.cuda.Event()
+        ready = torch.cuda.Event(enable_timing=self.trace is not None)
         ready.record(cur)
         self.stream.wait_event(ready)
         self.seq += 1
         L = self._lib.lib()
-        self._lib.check(L.delora_grad_allreduce_f32(self.peer_bufs, self.peer_flags, self.multicast, self.rank, self.world,
-                                                    start, end - start, 1.0 / self.world, self.seq & 0x7fffffff,
-                                                    self.n_ctas, self.status.data_ptr(), self.stream.cuda_stream),
-                        "delora_grad_allreduce_f32")
-        self._done = torch.cuda.Event()
+        if self.trace is not None:
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record(self.stream)
+        if not self.noop:
+            self._lib.check(L.delora_grad_allreduce_f32(self.peer_bufs, self.peer_flags, self.multicast, self.rank,
+                                                        self.world, start, end - start, 1.0 / self.world,
+                                                        self.seq & 0x7fffffff, self.n_ctas, self.n_threads,
+                                                        self.status.data_ptr(), self.stream.cuda_stream),
+                            "delora_grad_allreduce_f32")
+        self._done = torch.cuda.Event(enable_timing=self.trace is not None)
         self._done.record(self.stream)
+        if self.trace is not None:
+            self.trace.append((start, end, ready, t0, self._done))
 
     def wait(self):
         if self._done is not None:
@@ -160,7 +171,10 @@ class BucketedGradAllReduce:
         align = _PeerTransport.BUCKET_ALIGN
         total = sum((sum(p.numel() for p in b) + align - 1) // align * align for b in self.buckets)
         self.peer, self.transport, self.transport_note = None, "nccl", ""
-        if self.world > 1 and self.enabled and transport != "nccl" and device.type == "cuda":
+        # DELORA_AR_SELF=1 (experiments): run the peer kernel even in a one-rank group, to separate its own cost
+        # (launches, co-residency with the convolutions) from the coupling between ranks
+        solo = self.world == 1 and os.environ.get("DELORA_AR_SELF") == "1" and dist.is_initialized()
+        if (self.world > 1 or solo) and self.enabled and transport != "nccl" and device.type == "cuda":
             ok = 1
             try:
                 self.peer = _PeerTransport(total, device, process_group)
@@ -224,7 +238,7 @@ class BucketedGradAllReduce:
         if self._launched[bi]:
             return
         self._launched[bi] = True
-        if self.world == 1 or not self.enabled:
+        if (self.world == 1 and self.peer is None) or not self.enabled:
             return
         s, e = self.ranges[bi]
         if e == s:

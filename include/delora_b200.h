@@ -345,11 +345,12 @@ int delora_quat_to_T_bwd(const float* quaternion, const float* grad_T, int B,
  * scale: applied to the sum (1 / world for the average).  status: device int32, set non-zero if a peer did not arrive
  *   within 20 s (the kernel then carries on; it never hangs).  The kernel needs no shared memory and few registers so
  *   that its n_ctas CTAs are resident NEXT TO the persistent convolution CTAs and the reduction overlaps the backward.
- * Every rank must call it with the same offset / count / seq / n_ctas. */
+ * n_ctas CTAs (<= 160) of n_threads threads (32 .. 128).
+ * Every rank must call it with the same offset / count / seq / n_ctas / n_threads. */
 int delora_grad_allreduce_flag_words(void);
 int delora_grad_allreduce_f32(const uint64_t* peer_bufs, const uint64_t* peer_flags, uint64_t multicast_ptr, int rank,
                               int world, long long offset, long long count, float scale, uint32_t seq, int n_ctas,
-                              int32_t* status, void* stream);
+                              int n_threads, int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }

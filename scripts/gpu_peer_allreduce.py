@@ -81,14 +81,14 @@ if "--train" in sys.argv:
         pts[i, :, :n1] = s1[:, :n1]; pts[B + i, :, :n2] = s2[:, :n2]
         cnt[i], cnt[B + i] = n1, n2
     res = {}
-    for mode in ("bucketed", "bucketed-nccl", "none", "bucketed"):
+    for mode in ("bucketed", "bucketed-nccl", "none", "bucketed", "bucketed-nccl", "none"):
         torch.manual_seed(0)
         ts = SyntheticTrainStep(cfg, B, n_max, grad_sync=mode)
         ts.load(pts.to(dev), cnt.to(dev))
         for _ in range(3): loss, _ = ts.step()
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        K = 20
+        K = 40
         e0.record()
         for _ in range(K): loss, _ = ts.step()
         e1.record(); torch.cuda.synchronize()
@@ -101,6 +101,15 @@ if "--train" in sys.argv:
             ts.sync.peer.check()
         say(f"train step [{mode:13s}] transport {getattr(ts.sync, 'transport', '-'):15s}: {t.item():.3f} ms/step, loss {loss.item():.6f}, "
             f"weights identical across ranks: {all(torch.equal(wl[0], x) for x in wl)} {getattr(ts.sync, 'transport_note', '')}")
+        if getattr(ts.sync, "peer", None) is not None and mode == "bucketed":
+            # where inside the step each bucket's reduction ran: offsets relative to the step's first kernel
+            ts.sync.peer.trace = []
+            s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+            s0.record(); ts.step(); s1.record(); torch.cuda.synchronize()
+            for (a, b, ready, t0, t1) in ts.sync.peer.trace:
+                say(f"    bucket [{a:9d}, {b:9d}) {4*(b-a)/1e6:6.2f} MB: ready at {s0.elapsed_time(ready):.3f} ms, kernel "
+                    f"{s0.elapsed_time(t0):.3f} -> {s0.elapsed_time(t1):.3f} ms (step ends {s0.elapsed_time(s1):.3f})")
+            ts.sync.peer.trace = None
         del ts
         torch.cuda.empty_cache()
 dist.destroy_process_group()

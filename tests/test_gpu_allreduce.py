@@ -34,13 +34,13 @@ def _run(world, total, ranges, n_ctas, rounds=1, seed=0):
                 want[q][s:e] = acc
             for r in range(world):
                 _lib.check(L.delora_grad_allreduce_f32(pb, pf, 0, r, world, s, e - s, 1.0 / world, seq, n_ctas,
-                                                       status.data_ptr(), streams[r].cuda_stream), "grad_allreduce")
+                                                       128 if n_ctas <= 8 else 32, status.data_ptr(), streams[r].cuda_stream), "grad_allreduce")
     torch.cuda.synchronize()
     assert int(status.item()) == 0, "a rank timed out"
     return bufs, want
 
 
-@pytest.mark.parametrize("world,n_ctas", [(1, 4), (2, 8), (4, 16), (8, 4)])
+@pytest.mark.parametrize("world,n_ctas", [(1, 4), (2, 8), (4, 16), (8, 4), (2, 148)])
 def test_peer_allreduce_average_is_exact_and_identical_on_all_ranks(world, n_ctas, cuda_lib):
     total = 1 << 20
     ranges = [(0, 4096), (4096, 4096 + 300 * 128), (524288, 1 << 20), (262144, 262144 + 4)]
@@ -58,7 +58,8 @@ def test_peer_allreduce_rejects_bad_arguments(cuda_lib):
     status = torch.zeros(1, dtype=torch.int32, device=DEV)
     u64 = ctypes.c_uint64 * 1
     pb, pf = u64(buf.data_ptr()), u64(flags.data_ptr())
-    assert L.delora_grad_allreduce_f32(pb, pf, 0, 0, 1, 2, 64, 1.0, 1, 4, status.data_ptr(), None) != 0     # offset % 4
-    assert L.delora_grad_allreduce_f32(pb, pf, 0, 0, 1, 0, 64, 1.0, 1, 0, status.data_ptr(), None) != 0     # n_ctas
-    assert L.delora_grad_allreduce_f32(pb, pf, 0, 1, 1, 0, 64, 1.0, 1, 4, status.data_ptr(), None) != 0     # rank >= world
+    assert L.delora_grad_allreduce_f32(pb, pf, 0, 0, 1, 2, 64, 1.0, 1, 4, 128, status.data_ptr(), None) != 0     # offset % 4
+    assert L.delora_grad_allreduce_f32(pb, pf, 0, 0, 1, 0, 64, 1.0, 1, 0, 128, status.data_ptr(), None) != 0     # n_ctas
+    assert L.delora_grad_allreduce_f32(pb, pf, 0, 1, 1, 0, 64, 1.0, 1, 4, 128, status.data_ptr(), None) != 0     # rank >= world
+    assert L.delora_grad_allreduce_f32(pb, pf, 0, 0, 1, 0, 64, 1.0, 1, 4, 48, status.data_ptr(), None) != 0      # n_threads
     assert b"grad_allreduce" in L.delora_last_error()
