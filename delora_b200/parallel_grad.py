@@ -152,6 +152,8 @@ class BucketedGradAllReduce:
         self.enabled = bool(enabled)
         if transport not in ("auto", "peer", "nccl"):
             raise ValueError(f"transport must be auto, peer or nccl, got {transport!r}")
+        if transport == "peer" and not torch.cuda.is_available():
+            raise ValueError("transport='peer' needs CUDA devices on one NVLink node")
         params = [p for p in module.parameters() if p.requires_grad]
         trunk = list(encoder.trunk_parameters()) if encoder is not None else []
         trunk_ids = {id(p) for p in trunk}

@@ -234,6 +234,32 @@ def test_bucketed_overlapped_allreduce_world_size_2_gloo(tmp_path):
         opt.step()
 
 
+def test_bucket_layout_and_transport_arguments():
+    """Flat gradient buffer: buckets start on 128-float boundaries (the peer-memory kernel moves 16-byte vectors and
+    splits a bucket between the ranks), the views tile the buckets without overlap; transport names are checked and
+    the peer transport is refused without CUDA."""
+    from delora_b200.parallel_grad import BucketedGradAllReduce
+    model = _FakeModel()
+    sync = BucketedGradAllReduce(model, encoder=model.trunk)
+    assert sync.transport == "nccl" and sync.peer is None          # one process, CPU: nothing to rendezvous with
+    assert all(s % 128 == 0 and e % 128 == 0 and e > s for s, e in sync.ranges)
+    assert sync.ranges[-1][1] == sync.flat.numel()
+    base, seen = sync.flat.data_ptr(), []
+    for bi, bucket in enumerate(sync.buckets):
+        s, e = sync.ranges[bi]
+        for p in bucket:
+            off = (sync.views[id(p)].data_ptr() - base) // 4
+            assert s <= off and off + p.numel() <= e
+            seen.append((off, off + p.numel()))
+    seen.sort()
+    assert all(a[1] <= b[0] for a, b in zip(seen, seen[1:]))
+    with pytest.raises(ValueError):
+        BucketedGradAllReduce(_FakeModel(), transport="smoke-signals")
+    if not torch.cuda.is_available():
+        with pytest.raises(ValueError):
+            BucketedGradAllReduce(_FakeModel(), transport="peer")
+
+
 def test_kitti_bin_reader(tmp_path):
     """`data.kitti_scans.KITTIPointCloudDataset`: sorted *.bin files -> [4, N] float32 (src/data/kitti_scans.py:35-50)."""
     from delora_b200 import synthetic
