@@ -214,6 +214,7 @@ stem_weight_prep_kernel(const float* __restrict__ w, int Cin, __nv_bfloat16* __r
 // All filters of the encoder in ONE launch: table[l] = {fp32 weight ptr, fwd ptr, flip ptr, Cout, Cin, k, Cin_pad, kind}
 // (int64 each; kind 0 = the two layouts of weight_prep_kernel (conv_tc.cu), kind 1 = the stem layout above).
 // blockIdx.y = layer, blockIdx.x strides over the layer's elements.
+constexpr int kPrepTile = 32;
 __global__ void __launch_bounds__(256)
 weight_prep_multi_kernel(const long long* __restrict__ table) {
     const long long* e = table + (size_t)blockIdx.y * 8;
@@ -228,6 +229,37 @@ weight_prep_multi_kernel(const long long* __restrict__ table) {
             const int q = kk >> 4, c = kk & 15;
             const int cr = c & 7;
             w_fwd[i] = __float2bfloat16_rn((q < 3 && cr < Cin) ? __ldg(w + ((size_t)co * Cin + cr) * 9 + r * 3 + q) : 0.0f);
+        }
+        return;
+    }
+    if (Cout % kPrepTile == 0 && Cin % kPrepTile == 0 && Cin_pad == Cin && taps <= 9) {
+        // Tiled transposes: a (32 co x 32 ci x taps) block is read as 32 contiguous runs of 32 * taps floats, parked in
+        // shared memory (row stride 32 * 9 + 1: both read-outs are bank-conflict free) and written as 64-byte runs of
+        // both layouts.  The element-wise form below read every 32-byte sector of the fp32 filter 8 times per layout
+        // through L2 (124 us for the 11.7 M weights of the encoder; this form: one pass at streaming speed).
+        __shared__ float tile[kPrepTile * (kPrepTile * 9 + 1)];
+        constexpr int RS = kPrepTile * 9 + 1;
+        const int run = kPrepTile * taps;
+        const int tiles_ci = Cin / kPrepTile, n_tiles = (Cout / kPrepTile) * tiles_ci;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int co0 = (t / tiles_ci) * kPrepTile, ci0 = (t % tiles_ci) * kPrepTile;
+            __syncthreads();
+            for (int i = threadIdx.x; i < kPrepTile * run; i += 256) {
+                const int co = i / run, r = i - co * run;
+                tile[co * RS + r] = __ldg(w + ((size_t)(co0 + co) * Cin + ci0) * taps + r);
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < kPrepTile * run; i += 256) {
+                const int ci = i % kPrepTile, tap = (i / kPrepTile) % taps, co = i / run;
+                w_fwd[((size_t)(co0 + co) * taps + tap) * Cin_pad + ci0 + ci] = __float2bfloat16_rn(tile[co * RS + ci * taps + tap]);
+            }
+            if (w_flip) {
+                for (int i = threadIdx.x; i < kPrepTile * run; i += 256) {
+                    const int co = i % kPrepTile, tap = (i / kPrepTile) % taps, ci = i / run;
+                    w_flip[((size_t)(ci0 + ci) * taps + tap) * Cout + co0 + co] =
+                        __float2bfloat16_rn(tile[co * RS + ci * taps + (taps - 1 - tap)]);
+                }
+            }
         }
         return;
     }
@@ -285,7 +317,7 @@ extern "C" int delora_stem_weight_prep_bf16(const float* w, int Cin, void* w_ste
 
 extern "C" int delora_conv_weight_prep_multi(const void* table, int n_layers, void* stream) {
     DELORA_CHECK_ARG(table && n_layers >= 1 && n_layers <= 65535, "delora_conv_weight_prep_multi: bad argument");
-    weight_prep_multi_kernel<<<dim3(592, (unsigned)n_layers), 256, 0, (cudaStream_t)stream>>>((const long long*)table);
+    weight_prep_multi_kernel<<<dim3(296, (unsigned)n_layers), 256, 0, (cudaStream_t)stream>>>((const long long*)table);
     DELORA_CHECK_LAUNCH("weight_prep_multi_kernel");
     return 0;
 }

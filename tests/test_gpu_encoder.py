@@ -268,3 +268,29 @@ def test_maxpool_forward_argmax_and_backward(h, w, f16, act, cuda_lib):
     out = dz[:, 1:h + 1, 1:w + 1].float()
     assert torch.allclose(out, want, rtol=2 ** -7, atol=1e-6)
     assert torch.equal(dz[:, 1:h + 1, 0], dz[:, 1:h + 1, w]) and torch.equal(dz[:, 1:h + 1, w + 1], dz[:, 1:h + 1, 1])
+
+
+def test_weight_prep_multi_matches_per_layer_prep(cuda_lib):
+    """One launch for all filters (tiled transposes through shared memory for channel counts that are multiples of 32,
+    element-wise otherwise) against the single-layer kernel: both bf16 layouts bit for bit, 3x3 and 1x1, padded Cin."""
+    from delora_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(5)
+    shapes = [(64, 64, 3, 64), (128, 64, 3, 64), (128, 64, 1, 64), (512, 256, 3, 256), (512, 512, 3, 512), (64, 8, 3, 64),
+              (96, 32, 3, 32), (48, 24, 1, 64)]
+    rows, keep = [], []
+    for (cout, cin, k, cin_pad) in shapes:
+        w = torch.randn((cout, cin, k, k), generator=g, device=DEV)
+        fwd = torch.full((cout, k * k, cin_pad), 3.0, dtype=torch.bfloat16, device=DEV)
+        flip = torch.full((cin, k * k, cout), 3.0, dtype=torch.bfloat16, device=DEV) if k == 3 else None
+        ref_fwd, ref_flip = torch.empty_like(fwd), (torch.empty_like(flip) if flip is not None else None)
+        ops.conv_weight_prep(w, ref_fwd, ref_flip, cin_pad)
+        rows.append([w.data_ptr(), fwd.data_ptr(), flip.data_ptr() if flip is not None else 0, cout, cin, k, cin_pad, 0])
+        keep.append((w, fwd, flip, ref_fwd, ref_flip))
+    table = torch.tensor(rows, dtype=torch.int64, device=DEV)
+    ops.conv_weight_prep_multi(table, len(rows))
+    for (w, fwd, flip, ref_fwd, ref_flip) in keep:
+        assert torch.equal(fwd, ref_fwd), tuple(w.shape)
+        assert torch.equal(fwd[:, :, :w.shape[1]].float(),
+                           w.to(torch.bfloat16).float().permute(0, 2, 3, 1).reshape(fwd.shape[0], -1, w.shape[1]))
+        if flip is not None:
+            assert torch.equal(flip, ref_flip), tuple(w.shape)
