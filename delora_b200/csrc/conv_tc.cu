@@ -744,6 +744,41 @@ avgpool_bwd_act_kernel(const float* __restrict__ g, const __nv_bfloat16* __restr
     if (w == W - 1) reinterpret_cast<uint4*>(dz + (pix - W) * C)[grp] = out;
 }
 
+// AdaptiveAvgPool2d((1,1)) of the last feature map (src/models/resnet_modified.py:111): padded NHWC bf16 -> [B, C] fp32.
+// One CTA = 64 channels of one image; 32 pixel lanes x 8 channel groups (16-byte loads, 128-byte runs per pixel),
+// fp32 sums in a fixed order (deterministic), mean = sum / (H W).  Replaces slice -> .float() -> mean (two kernels,
+// 50 MB of traffic for the 16.8 MB map at B = 16).
+__global__ void __launch_bounds__(256)
+avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int H, int W, int C, float* __restrict__ y) {
+    __shared__ float part[32][65];
+    const int b = blockIdx.y, c0 = blockIdx.x * 64;
+    const int grp = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = 0.0f;
+    const int HW = H * W;
+    for (int p = pl; p < HW; p += 32) {
+        const int h = p / W, w = p - h * W;
+        const size_t pix = ((size_t)b * (H + 2) + h + 1) * (W + 2) + w + 1;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + pix * C + c0) + grp);
+        const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(v2[e]);
+            s[2 * e] += f.x; s[2 * e + 1] += f.y;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[pl][grp * 8 + e] = s[e];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float t = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) t += part[k][threadIdx.x];
+        y[(size_t)b * C + c0 + threadIdx.x] = t / (float)HW;
+    }
+}
+
 // padded NHWC bf16 -> NCHW fp32 (interior only): the reference's feature-map layout, for checks / heads
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, float* __restrict__ y) {
@@ -1094,6 +1129,15 @@ extern "C" int delora_avgpool_bwd_nhwc_bf16(const float* g, const void* a, int B
     avgpool_bwd_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         g, (const __nv_bfloat16*)a, B, H, W, C, act, (__nv_bfloat16*)dz);
     DELORA_CHECK_LAUNCH("avgpool_bwd_act_kernel");
+    return 0;
+}
+
+extern "C" int delora_avgpool_nhwc_bf16(const void* x, int B, int H, int W, int C, float* y, void* stream) {
+    DELORA_CHECK_ARG(x && y && B > 0 && B <= 65535 && H > 0 && W > 0 && C > 0 && C % 64 == 0,
+                     "delora_avgpool_nhwc_bf16: bad argument (C must be a multiple of 64, got %d)", C);
+    avgpool_nhwc_kernel<<<dim3((unsigned)(C / 64), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, H, W, C, y);
+    DELORA_CHECK_LAUNCH("avgpool_nhwc_kernel");
     return 0;
 }
 

@@ -38,6 +38,11 @@ class _EncoderTrainFn(torch.autograd.Function):
         grads = ctx.enc._backward(ctx.state, g_pooled.float().contiguous())
         ctx.state["slot"].release()
         ctx.state = None
+        if ctx.enc.grad_views is not None:
+            # the kernels wrote the weight gradients into the synchroniser's flat buffer and announced them
+            # (grad_ready); handing the same tensors to autograd as well would make AccumulateGrad clone each view
+            # (20 device copies, 47.5 MB per step) into a p.grad that finish() replaces by the view anyway
+            return (None, None, None) + (None,) * len(grads)
         return (None, None, None) + tuple(grads)
 
 
@@ -214,7 +219,7 @@ class TensorCoreEncoder:
         """(translation [B,3], quaternion [B,4]) like OdometryModel.forward (src/models/model.py:103-116)."""
         feats = self.features(image_1, image_2)
         x4, h4, w4 = feats[-1]
-        pooled = x4[:, 1:h4 + 1, 1:w4 + 1, :].float().mean(dim=(1, 2))           # AdaptiveAvgPool2d((1,1))
+        pooled = ops.avgpool(x4, h4, w4)                                          # AdaptiveAvgPool2d((1,1))
         m = self.model
         out = m.resnet.fc(pooled)
         if m.config["use_single_mlp_at_output"]:
@@ -311,7 +316,7 @@ class TensorCoreEncoder:
                                  "in_hw": (ch, cw), "out_hw": (oh, ow)})
             cur, ch, cw = out, oh, ow
         st["w_stem"] = w_stem
-        st["pooled"] = cur[:, 1:ch + 1, 1:cw + 1, :].float().mean(dim=(1, 2))
+        st["pooled"] = ops.avgpool(cur, ch, cw)
         return st
 
     def _backward(self, st, g_pooled):

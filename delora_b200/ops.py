@@ -405,6 +405,16 @@ def maxpool_w(x, h, w):
     return y
 
 
+def avgpool(x, h, w):
+    """AdaptiveAvgPool2d((1,1)) of a padded NHWC bf16 map -> [B, C] fp32."""
+    b, _, _, c = x.shape
+    y = torch.empty((b, c), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    _lib.check(L.delora_avgpool_nhwc_bf16(_req(x, torch.bfloat16, "x"), b, h, w, c, y.data_ptr(), _stream()),
+               "delora_avgpool_nhwc_bf16")
+    return y
+
+
 def nhwc_to_nchw(x, h, w):
     b, _, _, c = x.shape
     y = torch.empty((b, c, h, w), dtype=torch.float32, device=x.device)

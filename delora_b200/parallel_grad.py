@@ -140,7 +140,8 @@ class _PeerTransport:
 
 
 class BucketedGradAllReduce:
-    """Flat gradient buffer + bucketed, overlapped all-reduce.  Usage per step:
+    """Flat gradient buffer + bucketed, overlapped all-reduce.  Usage per step (ONE backward per step: the flat slices
+    are overwritten, not accumulated into):
         optimizer.zero_grad(set_to_none=True); loss.backward(); sync.finish(); optimizer.step()
     `finish()` waits for the outstanding collectives (stream-ordered, no host sync) and makes every `p.grad` the
     view of the flat buffer that holds the averaged gradient.  With WORLD_SIZE == 1 the buffer and the direct
@@ -273,7 +274,7 @@ class BucketedGradAllReduce:
         for bi in range(len(self.buckets)):        # parameters that received no gradient this step count as zeros
             if not self._launched[bi]:
                 for p in self.buckets[bi]:
-                    if p.grad is None:
+                    if id(p) not in self._ready:
                         self.views[id(p)].zero_()
                 self._launch(bi)
         for work, chunk in self._works:

@@ -321,6 +321,9 @@ int delora_maxpool_w_bwd_nhwc_bf16(const void* dy, const void* idx, const void* 
                                    void* dz, int a_f16, void* stream);
 int delora_avgpool_bwd_nhwc_bf16(const float* g, const void* a, int B, int H, int W, int C, int act, void* dz,
                                  void* stream);
+/* AdaptiveAvgPool2d((1,1)) (src/models/resnet_modified.py:111): padded NHWC bf16 [B,H+2,W+2,C] -> y [B,C] fp32
+ * (fp32 sums in a fixed order; C a multiple of 64) */
+int delora_avgpool_nhwc_bf16(const void* x, int B, int H, int W, int C, float* y, void* stream);
 /* padded NHWC bf16 -> NCHW fp32 (interior), the reference's feature-map layout */
 int delora_nhwc_to_nchw_f32(const void* x, int B, int H, int W, int C, float* y, void* stream);
 

@@ -294,3 +294,18 @@ def test_weight_prep_multi_matches_per_layer_prep(cuda_lib):
                            w.to(torch.bfloat16).float().permute(0, 2, 3, 1).reshape(fwd.shape[0], -1, w.shape[1]))
         if flip is not None:
             assert torch.equal(flip, ref_flip), tuple(w.shape)
+
+
+@pytest.mark.parametrize("b,h,w,c", [(2, 16, 64, 512), (1, 5, 23, 64), (3, 1, 1, 128)])
+def test_avgpool_matches_torch_mean(b, h, w, c, cuda_lib):
+    """AdaptiveAvgPool2d((1,1)) on the padded NHWC bf16 map (resnet_modified.py:111): fp32 mean of the bf16 values;
+    the halo must not leak into the sum."""
+    from delora_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(b * 100 + w)
+    x = torch.randn((b, h + 2, w + 2, c), generator=g, device=DEV).to(torch.bfloat16)       # halo filled with junk
+    got = ops.avgpool(x, h, w)
+    want = x[:, 1:h + 1, 1:w + 1].double().mean(dim=(1, 2))
+    assert got.shape == (b, c) and got.dtype == torch.float32
+    assert torch.allclose(got.double(), want, rtol=1e-5, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        ops.avgpool(torch.zeros((1, 3, 3, 40), dtype=torch.bfloat16, device=DEV), 1, 1)
