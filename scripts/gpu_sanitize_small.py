@@ -48,3 +48,18 @@ if "noenc" not in sys.argv:
     (t.sum() + qq.sum()).backward()
     torch.cuda.synchronize()
     print("encoder forward + backward done", float(t.abs().sum()))
+# peer-memory gradient all-reduce kernel, one-rank form (flags, vector loop, tail): the multi-rank protocol needs
+# concurrently resident kernels, which the sanitizer's serialisation does not give (tests/test_gpu_allreduce.py)
+import ctypes  # noqa: E402
+from delora_b200 import _lib  # noqa: E402
+L = _lib.lib()
+buf = torch.randn(5000 * 4, device="cuda")
+want = buf.clone() * 0.5
+flags = torch.zeros(L.delora_grad_allreduce_flag_words(), dtype=torch.int32, device="cuda")
+status = torch.zeros(1, dtype=torch.int32, device="cuda")
+u64 = ctypes.c_uint64 * 1
+_lib.check(L.delora_grad_allreduce_f32(u64(buf.data_ptr()), u64(flags.data_ptr()), 0, 0, 1, 0, buf.numel(), 0.5, 1, 3, 64,
+                                       status.data_ptr(), None), "grad_allreduce")
+torch.cuda.synchronize()
+assert torch.equal(buf, want) and int(status.item()) == 0
+print("grad all-reduce (one rank) done")
