@@ -15,6 +15,7 @@
 // The kernel is FP32-pipe / issue bound (~2.4 kFLOP per pixel against 28 B of HBM traffic), not HBM
 // bound: bench.py reports it against the fp32 roofline; see DESIGN.md.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace delora {
 
@@ -96,26 +97,12 @@ constexpr int kFastThreads = kFastTW * (kFastTH / kFastPix);            // 256
 constexpr int kFastTileW = kFastTW + 2 * kFastB;                        // 42
 constexpr int kFastTileH = kFastTH + 2 * kFastA;                        // 22
 
-__global__ void __launch_bounds__(kFastThreads)
-normals_7x11_kernel(const float* __restrict__ image, int C_img, int H, int W, float eps_range, int min_nb,
-                    float* __restrict__ normals, float4* __restrict__ pts_grid, float4* __restrict__ nrm_grid) {
-    __shared__ float4 tile[kFastTileH * kFastTileW];
-    const int bi = blockIdx.z;
-    const int u0 = blockIdx.x * kFastTW, v0 = blockIdx.y * kFastTH;
+// Everything after the staging: the tap loop, the eigen-solve and the stores (shared by both staging variants).
+__device__ __forceinline__ void normals_7x11_body(const float4* __restrict__ tile, int bi, int u0, int v0, int H, int W,
+                                                  float eps_range, int min_nb, float* __restrict__ normals,
+                                                  float4* __restrict__ pts_grid, float4* __restrict__ nrm_grid) {
     const size_t HW = (size_t)H * W;
-    const float* __restrict__ img = image + (size_t)bi * C_img * HW;
     const float inf = __int_as_float(0x7f800000);
-
-    for (int i = threadIdx.x; i < kFastTileH * kFastTileW; i += kFastThreads) {
-        const int ly = i / kFastTileW, lx = i - ly * kFastTileW;
-        const int gv = min(max(v0 - kFastA + ly, 0), H - 1), gu = min(max(u0 - kFastB + lx, 0), W - 1);
-        const size_t o = (size_t)gv * W + gu;
-        const float x = __ldg(img + o), y = __ldg(img + HW + o), z = __ldg(img + 2 * HW + o);
-        const bool zero = (x == 0.0f) & (y == 0.0f) & (z == 0.0f);
-        tile[i] = make_float4(x, y, z, zero ? inf : range3(x, y, z));
-    }
-    __syncthreads();
-
     const int lu = threadIdx.x % kFastTW, lr = threadIdx.x / kFastTW;       // lr: which group of 4 rows
     const int u = u0 + lu, vb = v0 + lr * kFastPix;
     if (u >= W || vb >= H) return;
@@ -222,6 +209,66 @@ normals_7x11_kernel(const float* __restrict__ image, int C_img, int H, int W, fl
     }
 }
 
+// Staging variant 1 (default): coalesced loads, index clamp, repack -- all in one pass.
+__global__ void __launch_bounds__(kFastThreads)
+normals_7x11_kernel(const float* __restrict__ image, int C_img, int H, int W, float eps_range, int min_nb,
+                    float* __restrict__ normals, float4* __restrict__ pts_grid, float4* __restrict__ nrm_grid) {
+    __shared__ float4 tile[kFastTileH * kFastTileW];
+    const int bi = blockIdx.z;
+    const int u0 = blockIdx.x * kFastTW, v0 = blockIdx.y * kFastTH;
+    const size_t HW = (size_t)H * W;
+    const float* __restrict__ img = image + (size_t)bi * C_img * HW;
+    const float inf = __int_as_float(0x7f800000);
+
+    for (int i = threadIdx.x; i < kFastTileH * kFastTileW; i += kFastThreads) {
+        const int ly = i / kFastTileW, lx = i - ly * kFastTileW;
+        const int gv = min(max(v0 - kFastA + ly, 0), H - 1), gu = min(max(u0 - kFastB + lx, 0), W - 1);
+        const size_t o = (size_t)gv * W + gu;
+        const float x = __ldg(img + o), y = __ldg(img + HW + o), z = __ldg(img + 2 * HW + o);
+        const bool zero = (x == 0.0f) & (y == 0.0f) & (z == 0.0f);
+        tile[i] = make_float4(x, y, z, zero ? inf : range3(x, y, z));
+    }
+    __syncthreads();
+    normals_7x11_body(tile, bi, u0, v0, H, W, eps_range, min_nb, normals, pts_grid, nrm_grid);
+}
+
+// Staging variant 2 (delora_normals_select_staging(1); built to MEASURE what TMA buys here): ONE
+// cp.async.bulk.tensor.4d box brings the three channel planes of the halo tile into shared memory (out-of-image
+// positions zero-filled), then the same repack as above runs from shared memory -- the edge clamp becomes a clamped
+// read of the planes, the zero test and |p| stay.  The tensor-map box cannot do that repack, so the pass over the
+// 22 x 42 positions remains; what TMA removes is the address arithmetic and the three global loads per position.
+// The box starts 8 (not 5) columns left of the tile: TMA wants the first element of a box row on a 16-byte boundary
+// (u0 - 5 faulted with "illegal instruction" on the UTMALDG), so the planes are 48 floats wide.
+constexpr int kFastPlaneOff = 8, kFastPlaneW = 48;
+__global__ void __launch_bounds__(kFastThreads)
+normals_7x11_tma_kernel(const __grid_constant__ CUtensorMap map_img, int H, int W, float eps_range, int min_nb,
+                        float* __restrict__ normals, float4* __restrict__ pts_grid, float4* __restrict__ nrm_grid) {
+    __shared__ __align__(128) float planes[3][kFastTileH][kFastPlaneW];
+    __shared__ float4 tile[kFastTileH * kFastTileW];
+    __shared__ __align__(8) uint64_t bar;
+    const int bi = blockIdx.z;
+    const int u0 = blockIdx.x * kFastTW, v0 = blockIdx.y * kFastTH;
+    const float inf = __int_as_float(0x7f800000);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(&bar, (uint32_t)sizeof(planes));
+        tma_load_4d(&planes[0][0][0], &map_img, &bar, u0 - kFastPlaneOff, v0 - kFastA, 0, bi);
+    }
+    __syncthreads();                                                     // barrier initialised before anybody polls it
+    mbar_wait(&bar, 0);
+    for (int i = threadIdx.x; i < kFastTileH * kFastTileW; i += kFastThreads) {
+        const int ly = i / kFastTileW, lx = i - ly * kFastTileW;
+        const int sv = min(max(v0 - kFastA + ly, 0), H - 1) - (v0 - kFastA);     // the reference's index clamp, in tile
+        const int su = min(max(u0 - kFastB + lx, 0), W - 1) - (u0 - kFastPlaneOff);   // coordinates (always inside the box)
+        const float x = planes[0][sv][su], y = planes[1][sv][su], z = planes[2][sv][su];
+        const bool zero = (x == 0.0f) & (y == 0.0f) & (z == 0.0f);
+        tile[i] = make_float4(x, y, z, zero ? inf : range3(x, y, z));
+    }
+    __syncthreads();
+    normals_7x11_body(tile, bi, u0, v0, H, W, eps_range, min_nb, normals, pts_grid, nrm_grid);
+}
+
 // Generic patch sizes (and the first version of the kernel): one pixel per thread, runtime loops.
 // A, B: half sizes of the patch when known at compile time (loops unroll); -1 = runtime.
 template <int A_, int B_>
@@ -324,6 +371,13 @@ normals_kernel(const float* __restrict__ image, int C_img, int H, int W, int a_r
 
 using namespace delora;
 
+static int g_normals_staging = 0;      // 0: coalesced loads (default), 1: TMA box + repack from shared memory
+extern "C" int delora_normals_select_staging(int mode) {
+    const int old = g_normals_staging;
+    if (mode == 0 || mode == 1) g_normals_staging = mode;
+    return old;
+}
+
 extern "C" int delora_normals_fwd(const float* image, int B, int C_img, int H, int W, int nb_h, int nb_w,
                                   float epsilon_range, int min_neighbors, float* normals, delora_f4* pts_grid,
                                   delora_f4* nrm_grid, void* stream) {
@@ -338,8 +392,26 @@ extern "C" int delora_normals_fwd(const float* image, int B, int C_img, int H, i
     cudaStream_t st = (cudaStream_t)stream;
     if (a == kFastA && b == kFastB) {
         dim3 gridf((W + kFastTW - 1) / kFastTW, (H + kFastTH - 1) / kFastTH, B);
-        normals_7x11_kernel<<<gridf, kFastThreads, 0, st>>>(image, C_img, H, W, epsilon_range, min_neighbors, normals,
-                                                            (float4*)pts_grid, (float4*)nrm_grid);
+        bool tma_done = false;
+        if (g_normals_staging == 1 && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0) {
+            PFN_cuTensorMapEncodeTiled_v12000 encode = get_tensor_map_encoder();
+            DELORA_CHECK_ARG(encode != nullptr, "delora_normals_fwd: cuTensorMapEncodeTiled unavailable");
+            CUtensorMap m;
+            cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C_img, (cuuint64_t)B};
+            cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C_img * H * W * 4};
+            cuuint32_t box[4] = {(cuuint32_t)kFastPlaneW, (cuuint32_t)kFastTileH, 3, 1};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult rc = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(image), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            DELORA_CHECK_ARG(rc == CUDA_SUCCESS, "delora_normals_fwd: tensor map failed: %d", (int)rc);
+            normals_7x11_tma_kernel<<<gridf, kFastThreads, 0, st>>>(m, H, W, epsilon_range, min_neighbors, normals,
+                                                                    (float4*)pts_grid, (float4*)nrm_grid);
+            tma_done = true;
+        }
+        if (!tma_done)
+            normals_7x11_kernel<<<gridf, kFastThreads, 0, st>>>(image, C_img, H, W, epsilon_range, min_neighbors, normals,
+                                                                (float4*)pts_grid, (float4*)nrm_grid);
     } else {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(normals_kernel<-1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -105,6 +105,11 @@ int delora_sort_by_range(const float* range, const int32_t* n_points, int B, int
 int delora_normals_fwd(const float* image, int B, int C_img, int H, int W, int nb_h, int nb_w,
                        float epsilon_range, int min_neighbors, float* normals,
                        delora_f4* pts_grid, delora_f4* nrm_grid, void* stream);
+/* How the 7x11 kernel stages its halo tile: 0 (default) coalesced loads + clamp + repack in one pass; 1 one TMA box
+ * (cp.async.bulk.tensor.4d, three channel planes) + the same repack from shared memory (needs W % 4 == 0 and a 16-byte
+ * aligned image, else mode 0 is used).  Results are bit-identical; mode 1 exists to measure what TMA buys this kernel
+ * (DESIGN.md 4.2).  Returns the previous mode. */
+int delora_normals_select_staging(int mode);
 
 /* ---------------------------------------------------------------------------------------
  * Image -> lists (row-major order of the valid pixels), the layout the reference stores and
