@@ -4,9 +4,33 @@ Every function takes CUDA tensors, allocates its outputs with torch (device memo
 plumbing torch provides), passes raw pointers + the current stream to libdelora_b200.so and
 returns tensors.  Nothing here computes on the host and nothing falls back to torch ops.
 """
+import os
+
 import torch
 
 from . import _lib
+
+# NVTX ranges around the operators (SURVEY.md section 5, tracing): DELORA_NVTX=1 names the phases of a step for
+# nsys / ncu --nvtx; off by default (no push / pop calls at all on the hot path).
+NVTX = os.environ.get("DELORA_NVTX") == "1"
+
+
+class nvtx_range:
+    """`with ops.nvtx_range("normals"):` -- an NVTX range when DELORA_NVTX=1, otherwise nothing."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
 
 LOSS_PO2PO, LOSS_PO2PL, LOSS_PL2PL, NORMAL_LINEAR = 1, 2, 4, 8
 LOSS_ROW, ICP_PARTIAL = 8, 40

@@ -96,6 +96,15 @@ class ScanPairPipeline:
         """Enqueue the whole hot path on the current stream; returns (losses [B,8], grad_T [B,12]).
         `events`: optional list of 4 torch.cuda.Event (timing enabled) recorded before the first and
         after each of the three operators, for per-kernel timing inside a measured region."""
+        if ops.NVTX:
+            torch.cuda.nvtx.range_push("scan-pair step")
+            try:
+                return self._step(events)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return self._step(events)
+
+    def _step(self, events):
         if self._subs and events is None:
             return self._step_concurrent()
         L, st = self.L, torch.cuda.current_stream().cuda_stream

@@ -50,22 +50,28 @@ class SyntheticTrainStep:
 
     def step(self):
         b, h, w = self.B, self.H, self.W
-        image, _ = ops.project(self.points, self.n_points, h, w, self.hf, self.vf)
-        _, pts_grid, nrm_grid = ops.normals(image, self.cfg["kitti"]["neighborhood_side_length"],
-                                            self.cfg["epsilon_range"],
-                                            self.cfg["min_num_points_in_neighborhood_to_determine_point_class"],
-                                            grids=True)
+        with ops.nvtx_range("projection"):
+            image, _ = ops.project(self.points, self.n_points, h, w, self.hf, self.vf)
+        with ops.nvtx_range("normals"):
+            _, pts_grid, nrm_grid = ops.normals(image, self.cfg["kitti"]["neighborhood_side_length"],
+                                                self.cfg["epsilon_range"],
+                                                self.cfg["min_num_points_in_neighborhood_to_determine_point_class"],
+                                                grids=True)
         self.optimizer.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast_bf16):
-            translations, quaternions = self.model(image_1=image[:b].contiguous(), image_2=image[b:].contiguous())
-        translations, quaternions = translations.float(), quaternions.float()
-        T = GeometryHandler.get_transformation_matrix_quaternion(translations, quaternions, self.device)
-        total, parts = _FusedIcp.apply(T, pts_grid[b:].contiguous(), nrm_grid[b:].contiguous(),
-                                       pts_grid[:b].contiguous(), nrm_grid[:b].contiguous(),
-                                       (h, w, self.hf, self.vf), float(self.cfg["lambda_po2pl"]),
-                                       ops.LOSS_PO2PL | ops.LOSS_PL2PL, self.scratch)
-        loss = total.mean()
-        loss.backward()
-        self.sync.finish()
-        self.optimizer.step()
+        with ops.nvtx_range("model forward"):
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast_bf16):
+                translations, quaternions = self.model(image_1=image[:b].contiguous(), image_2=image[b:].contiguous())
+            translations, quaternions = translations.float(), quaternions.float()
+            T = GeometryHandler.get_transformation_matrix_quaternion(translations, quaternions, self.device)
+        with ops.nvtx_range("icp losses"):
+            total, parts = _FusedIcp.apply(T, pts_grid[b:].contiguous(), nrm_grid[b:].contiguous(),
+                                           pts_grid[:b].contiguous(), nrm_grid[:b].contiguous(),
+                                           (h, w, self.hf, self.vf), float(self.cfg["lambda_po2pl"]),
+                                           ops.LOSS_PO2PL | ops.LOSS_PL2PL, self.scratch)
+            loss = total.mean()
+        with ops.nvtx_range("backward (+ gradient buckets)"):
+            loss.backward()
+            self.sync.finish()
+        with ops.nvtx_range("optimizer"):
+            self.optimizer.step()
         return loss.detach(), parts

@@ -260,6 +260,23 @@ def test_bucket_layout_and_transport_arguments():
             BucketedGradAllReduce(_FakeModel(), transport="peer")
 
 
+def test_nvtx_ranges_are_opt_in(monkeypatch):
+    """`ops.nvtx_range` (DELORA_NVTX=1): pushes / pops a named range only when enabled; usable without a GPU."""
+    from delora_b200 import ops
+    calls = []
+    monkeypatch.setattr(torch.cuda.nvtx, "range_push", lambda name: calls.append(("push", name)))
+    monkeypatch.setattr(torch.cuda.nvtx, "range_pop", lambda: calls.append(("pop",)))
+    monkeypatch.setattr(ops, "NVTX", False)
+    with ops.nvtx_range("normals"):
+        pass
+    assert calls == []
+    monkeypatch.setattr(ops, "NVTX", True)
+    with pytest.raises(KeyError):
+        with ops.nvtx_range("normals"):
+            raise KeyError("propagates, range still closed")
+    assert calls == [("push", "normals"), ("pop",)]
+
+
 def test_kitti_bin_reader(tmp_path):
     """`data.kitti_scans.KITTIPointCloudDataset`: sorted *.bin files -> [4, N] float32 (src/data/kitti_scans.py:35-50)."""
     from delora_b200 import synthetic
