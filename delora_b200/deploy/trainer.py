@@ -104,6 +104,9 @@ class Trainer(deployer.Deployer):
                 t = torch.tensor([history[-1]], dtype=torch.float64, device=self.device)
                 torch.distributed.all_reduce(t)
                 history[-1] = float(t[0]) / self.grad_sync.world
+                peer = getattr(self.grad_sync, "peer", None)
+                if peer is not None:
+                    peer.check()        # a rank that missed a peer-memory collective this epoch is an error, not noise
             if self.grad_sync.rank == 0:
                 print("Epoch Summary: " + format(epoch, "05d") + ", loss: " + str(epoch_losses["loss_epoch"]) +
                       ", unsupervised: " + str(self.config["unsupervised_at_start"]))
